@@ -1,0 +1,154 @@
+/* vcb200.h — C ABI of the B200-native video-caption hot path.
+ *
+ * Drop-in boundary.  The reference is 100 % Python; its plugin
+ * surface for this path is (1) the module attributes `model.encoder(video)`,
+ * `model.decoder.mapper(x)`, `model.decoder.model(inputs_embeds=…, past_key_values=…)`
+ * used by core/engine.py:43-61 and core/scripts/benchmark_baseline.py:162-289,
+ * (2) the backend switch in core/models/model_loader.py:21-28 and (3) the CuPy
+ * operator hooks core/operators/cupy_vit_pool.py:127-186 and
+ * core/operators/cupy_linear_mapper.py:137-184.  A maintainer binds this library
+ * with ctypes; the Python adapter in
+ * video-caption-algorithm_b200/ presents surface (1) on top of it.
+ *
+ * Conventions (same as the reference's hooks): every pointer is DEVICE memory
+ * owned by the caller (torch), nothing is allocated inside, work is enqueued on
+ * the stream passed in (the reference uses torch's current stream:
+ * cupy_vit_pool.py:162-163), calls return 0 on success and a negative code on
+ * error with the text in vc_last_error().  Unlike the reference's hooks there is
+ * NO fallback: an error is an error (north_star: "no CPU fallback").
+ */
+#ifndef VCB200_H
+#define VCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* vc_stream_t; /* cudaStream_t */
+
+/* GEMM epilogues (vc_gemm_bf16) */
+enum {
+  VC_EPI_BIAS = 0,           /* bf16 out = acc + bias                                  */
+  VC_EPI_BIAS_GELU_ERF = 1,  /* bf16 out = gelu_erf(acc + bias)   torchvision nn.GELU() */
+  VC_EPI_BIAS_GELU_TANH = 2, /* bf16 out = gelu_tanh(acc + bias)  timm patch / gelu_new */
+  VC_EPI_BIAS_RESID_F32 = 3, /* fp32 out += acc + bias            residual stream       */
+  VC_EPI_BIAS_F32 = 4,       /* fp32 out = acc + bias                                  */
+  VC_EPI_PATCH_EMBED = 5     /* fp32 out[g*(rpg+1)+1+r] = acc + bias + pos[1+r]         */
+};
+
+/* ---- ViT encoder weights: packed once from the model state_dict ------------------------ */
+typedef struct {
+  const float* ln1_g; const float* ln1_b;   /* LayerNorm eps 1e-6 */
+  const void* qkv_w;  const float* qkv_b;   /* bf16 [3D, D], rows q|k|v (in_proj_weight / attn.qkv) */
+  const void* proj_w; const float* proj_b;  /* bf16 [D, D] */
+  const float* ln2_g; const float* ln2_b;
+  const void* fc1_w;  const float* fc1_b;   /* bf16 [mlp, D] */
+  const void* fc2_w;  const float* fc2_b;   /* bf16 [D, mlp] */
+} VcVitLayer;
+
+typedef struct {
+  int32_t dim, layers, heads, mlp, tokens, patch_k; /* patch_k: 3*p*p padded to a multiple of 64 */
+  int32_t gelu_tanh;                                 /* 0: erf (torchvision path) 1: tanh (timm path, video_encoder.py:134) */
+  int32_t video_dim;                                 /* 256 */
+  const void* patch_w;  const float* patch_b;        /* bf16 [dim, patch_k] (conv_proj flattened c,i,j) */
+  const float* cls_pos0;                             /* fp32 [dim]: class_token + pos_embedding[0] */
+  const float* pos;                                  /* fp32 [tokens, dim] */
+  const float* lnf_g; const float* lnf_b;            /* encoder.ln / norm */
+  const float* head_w; const float* head_b;          /* fp32 encoder.proj [video_dim, dim] */
+  const VcVitLayer* layer;                           /* host array [layers] */
+} VcVitWeights;
+
+/* ---- GPT-2 decoder weights --------------------------------------------------------------- */
+typedef struct {
+  const float* ln1_g; const float* ln1_b;    /* eps 1e-5 */
+  const void* attn_w;  const float* attn_b;  /* bf16 [3H, H] = c_attn.weight^T (Conv1D is [in,out]) */
+  const void* aproj_w; const float* aproj_b; /* bf16 [H, H]  = attn.c_proj.weight^T */
+  const float* ln2_g; const float* ln2_b;
+  const void* fc_w;    const float* fc_b;    /* bf16 [4H, H] */
+  const void* mproj_w; const float* mproj_b; /* bf16 [H, 4H] */
+} VcGptLayer;
+
+typedef struct {
+  int32_t dim, layers, heads, vocab, n_pos, vocab_pad; /* vocab_pad: rows of wte padded to a multiple of 64 (zero rows) */
+  const void* wte;            /* bf16 [vocab_pad, H] (tied lm_head) */
+  const float* wpe;           /* fp32 [n_pos, H] */
+  const float* lnf_g; const float* lnf_b;
+  const VcGptLayer* layer;    /* host array [layers] */
+} VcGptWeights;
+
+/* contiguous bf16 KV cache [layers][2][n_seq][heads][s_max][head_dim] + per-(seq,pos) slot table for beams */
+typedef struct {
+  void* kv;                 /* bf16 */
+  int32_t* slot;            /* int32 [n_seq, s_max]: physical sequence row holding position p of logical row s */
+  int32_t layers, n_seq, heads, s_max, head_dim;
+} VcKvCache;
+
+/* ---- library state ----------------------------------------------------------------------- */
+const char* vc_last_error(void);
+int vc_abi_version(void);
+int vc_num_sms(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+long long vc_launch_count(void);
+/* optional per-kernel CUDA-event timing on the launch stream (bench.py roofline pass) */
+int vc_prof_begin(void);
+int vc_prof_end(int max_rows, char* names /*[max_rows][48]*/, float* total_ms, int* calls, double* work);
+
+/* ---- a1  preprocessing: core/preprocessing/frame_loader.py:34-47 ------------------------ */
+/* uint8 HWC frames -> bf16 through the 3x256 LUT of ToTensor+Normalize.
+ * layout 0: [n,3,H,W] (the reference tensor, bf16-rounded); layout 1: patch-major
+ * [n*(H/p)*(W/p), k_pad] with column c*p*p + i*p + j — the A operand of the patch-embed GEMM. */
+int vc_preprocess_u8(const uint8_t* frames_hwc, const float* lut3x256, void* out_bf16, int n_frames, int H, int W,
+                     int layout, int patch, int k_pad, vc_stream_t stream);
+
+/* ---- a2  ViT encoder building blocks + whole encoder: src/models/video_encoder.py:288-326 */
+int vc_gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int K, int epilogue, void* out, int ldo,
+                 const float* aux, int rows_per_group, vc_stream_t stream);
+int vc_layernorm_f32_bf16(const float* x, const float* gamma, const float* beta, void* out_bf16, int rows, int dim,
+                          float eps, vc_stream_t stream);
+int vc_vit_attention(const void* qkv_bf16, void* out_bf16, int n_frames, int tokens, int heads, int head_dim,
+                     vc_stream_t stream);
+size_t vc_vit_workspace_bytes(const VcVitWeights* w, int chunk_frames);
+/* patches: bf16 [n_frames*(tokens-1), patch_k]; cls_out: fp32 [n_frames, dim] = final-LN class token per frame */
+int vc_vit_encode(const VcVitWeights* w, const void* patches_bf16, int n_frames, int chunk_frames, void* workspace,
+                  size_t workspace_bytes, float* cls_out, vc_stream_t stream);
+
+/* ---- a3-a6  pool + proj + prefix norm + mapper: video_encoder.py:256-258,316; engine.py:45-50;
+ *      text_decoder.py:36-45,69; replaces cupy_vit_pool.py / cupy_linear_mapper.py ---------- */
+int vc_pool_prefix(const float* cls_tokens /*[B*T, dim]*/, int B, int T, int dim, const float* head_w, const float* head_b,
+                   int video_dim, float ln_scale, float in_weight, const float* mapper_w /*[out, video_dim]*/,
+                   const float* mapper_b, int mapper_out, float* feat_out /*[B,video_dim]*/, float* prefix_out /*[B,mapper_out]*/,
+                   vc_stream_t stream);
+/* the two CuPy hooks as stand-alone operators (same contracts, torch-owned tensors) */
+int vc_vit_pool_temporal(const void* feat, int is_bf16, int bsz, int timesteps, int tokens, int channels, int gap,
+                         float* out /*[bsz,channels]*/, vc_stream_t stream);
+int vc_linear_bias_f32(const float* x, const float* w, const float* b, float* y, int rows, int in_features, int out_features,
+                       vc_stream_t stream);
+
+/* ---- a7-a9  GPT-2 forward with KV cache (transformers GPT2LMHeadModel.forward) ----------- */
+size_t vc_gpt_workspace_bytes(const VcGptWeights* w, int n_seq, int max_new_rows);
+/* rows = n_seq * L new positions (L>=1), fp32 embeds [n_seq, L, H] WITHOUT position embedding;
+ * past_len = positions already in the cache.  logits_out (fp32 [n_seq, vocab]) may be NULL;
+ * next_ids (int32 [n_seq]) = argmax of the last position (ties -> lowest index) may be NULL. */
+int vc_gpt2_forward(const VcGptWeights* w, const float* embeds, int n_seq, int L, int past_len, VcKvCache* cache,
+                    void* workspace, size_t workspace_bytes, float* logits_out, int32_t* next_ids, vc_stream_t stream);
+/* wte gather for fed-back tokens: out fp32 [n, H] */
+int vc_gpt2_embed_tokens(const VcGptWeights* w, const int32_t* ids, int n, float* out, vc_stream_t stream);
+
+/* ---- a8  greedy loop of core/scripts/benchmark_baseline.py:160-240, no host sync ---------- */
+/* prefix fp32 [n_seq, P, H]; prompt_ids int32 [Lp] (shared by all rows); ids_out int32 [n_seq, max_new]
+ * padded with eos; len_out int32 [n_seq]; forced_ids (teacher forcing, int32 [n_seq,max_new]) may be NULL;
+ * step_logits (fp32 [max_new, n_seq, vocab]) may be NULL. */
+int vc_greedy_decode(const VcGptWeights* w, const float* prefix, int n_seq, int P, const int32_t* prompt_ids, int Lp,
+                     int max_new, int eos, VcKvCache* cache, void* workspace, size_t workspace_bytes, int32_t* ids_out,
+                     int32_t* len_out, const int32_t* forced_ids, float* step_logits, vc_stream_t stream);
+
+/* ---- token selection on given logits (bit-exact vs torch.argmax / topk) ------------------- */
+int vc_argmax_f32(const float* logits, int rows, int vocab, int32_t* out, vc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCB200_H */

@@ -1,0 +1,67 @@
+"""Pins oracle/vc_oracle.py against the fixtures produced by the UNMODIFIED reference
+modules (oracle/pin_against_reference.py, run in the build container).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+import vcb200  # noqa: F401
+from vcb200 import synthetic
+from oracle import vc_oracle as O
+
+
+def test_frame_sampling_matches_reference(golden_dir):
+    g = np.load(golden_dir / "preprocess.npz")
+    assert O.sample_frame_indices(int(g["n_files"]), int(g["num_frames"])) == g["picked"].tolist()
+    # frame_loader.py:31-32 examples from SURVEY.md A.1
+    assert O.sample_frame_indices(40, 16) == list(range(0, 32, 2))
+    assert O.sample_frame_indices(10, 16) == list(range(10))
+    assert O.sample_frame_indices(1, 16) == [0]
+
+
+def test_preprocess_bit_exact_vs_reference(golden_dir):
+    g = np.load(golden_dir / "preprocess.npz")
+    u8 = torch.from_numpy(g["u8"])            # [4,32,48,3] decoded JPEG bytes
+    ref = torch.from_numpy(g["ref"])          # the reference's load_video_tensor output crop
+    assert torch.equal(O.preprocess_u8(u8), ref)
+    lut = O.normalize_lut()
+    via_lut = torch.stack([lut[c][u8[..., c].long()] for c in range(3)], dim=1)
+    assert torch.equal(via_lut, ref)
+
+
+@pytest.mark.parametrize("arch", ["tiny", "vit_b16_gpt2"])
+def test_path_matches_reference(golden_dir, arch):
+    g = np.load(golden_dir / f"path_{arch}.npz")
+    a = synthetic.ARCHS[arch]
+    sd = synthetic.make_state_dict(a, seed=int(g["seed"]))
+    frames = synthetic.make_batch_u8(0, int(g["B"]), int(g["T"]))
+    torch.set_num_threads(8)
+    video = O.preprocess_u8(frames)
+    feat = O.encode(sd, video, a.vit_heads)
+    ref_feat = torch.from_numpy(g["feat"])
+    assert (feat - ref_feat).abs().max().item() < 2e-5
+    prefix = O.visual_prefix(sd, feat)
+    assert (prefix - torch.from_numpy(g["prefix"])).abs().max().item() < 2e-5
+    prompt = torch.tensor([[50256]])
+    n_new = int(g["max_new_tokens"])
+    ids, lengths, logits = O.greedy_decode(sd, prefix, prompt, n_new, heads=a.gpt_heads, keep_logits=True)
+    assert ids.tolist() == g["ids"].tolist()
+    assert lengths.tolist() == g["lengths"].tolist()
+    L = torch.stack(logits, 0)
+    stride = int(g["logits_stride"])
+    assert (L[:, :, ::stride] - torch.from_numpy(g["logits_sub"])).abs().max().item() < 5e-4
+    assert torch.equal(L.topk(8, dim=-1).indices, torch.from_numpy(g["logits_top_idx"]))
+
+
+@pytest.mark.parametrize("arch,key,nb,mx", [("tiny", "beam3_24", 3, 24), ("tiny", "beam5_30", 5, 30),
+                                            ("vit_b16_gpt2", "beam5_30", 5, 30)])
+def test_beam_search_matches_hf_generate(golden_dir, arch, key, nb, mx):
+    g = np.load(golden_dir / f"path_{arch}.npz")
+    a = synthetic.ARCHS[arch]
+    sd = synthetic.make_state_dict(a, seed=int(g["seed"]))
+    prefix = torch.from_numpy(g["prefix"])
+    ids, lengths = O.beam_search(sd, prefix, torch.tensor([[50256]]), num_beams=nb, max_new_tokens=mx, heads=a.gpt_heads)
+    ref = g[key]                      # HF output: [B, longest], padded with eos
+    for b in range(ref.shape[0]):
+        n = int(lengths[b])
+        assert ids[b, :n].tolist() == ref[b, :n].tolist()
+        assert all(t == 50256 for t in ref[b, n:].tolist())

@@ -1,0 +1,288 @@
+// C-ABI entry points (include/vcb200.h) and the host-side orchestration of the two
+// hot loops: the ViT encoder over B*T frames (src/models/video_encoder.py:288-326)
+// and the GPT-2 forward / greedy loop (core/scripts/benchmark_baseline.py:160-240).
+// Everything is enqueued on the caller's stream; nothing here synchronises or allocates.
+#include "vc_common.cuh"
+#include "vc_kernels.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace vc {
+
+// ---------------------------------------------------------------- error text
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---------------------------------------------------------------- launch accounting / profiling
+static std::atomic<long long> g_launches{0};
+static bool g_prof_on = false;
+struct ProfRec { const char* name; double work; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;
+
+KernelScope::KernelScope(const char* name, double work, cudaStream_t stream) : stream_(stream), slot_(-1) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (g_prof_on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfRec r{name, work, nullptr, nullptr};
+    if (cudaEventCreate(&r.a) == cudaSuccess && cudaEventCreate(&r.b) == cudaSuccess) {
+      cudaEventRecord(r.a, stream);
+      g_prof.push_back(r);
+      slot_ = static_cast<int>(g_prof.size()) - 1;
+    }
+  }
+}
+KernelScope::~KernelScope() {
+  if (slot_ >= 0) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEventRecord(g_prof[slot_].b, stream_);
+  }
+}
+
+static inline cudaStream_t S(vc_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct VitBuffers {
+  float* x; void* xn; void* qkv; void* att; void* hid; size_t total;
+};
+static VitBuffers carve_vit(const VcVitWeights* w, int chunk_frames, void* base) {
+  const size_t M = static_cast<size_t>(chunk_frames) * w->tokens;
+  uint8_t* p = static_cast<uint8_t*>(base);
+  size_t off = 0;
+  VitBuffers b;
+  b.x = reinterpret_cast<float*>(p + off);  off += align_up(M * w->dim * 4, 1024);
+  b.xn = p + off;                           off += align_up(M * w->dim * 2, 1024);
+  b.qkv = p + off;                          off += align_up(M * w->dim * 3 * 2, 1024);
+  b.att = p + off;                          off += align_up(M * w->dim * 2, 1024);
+  b.hid = p + off;                          off += align_up(M * w->mlp * 2, 1024);
+  b.total = off;
+  return b;
+}
+
+struct GptBuffers {
+  float* h; void* xn; void* qkv; void* att; void* hid; float* emb; float* logits; int32_t* finished; int32_t* next; size_t total;
+};
+static GptBuffers carve_gpt(const VcGptWeights* w, int n_seq, int max_rows, void* base) {
+  const size_t R = static_cast<size_t>(max_rows);
+  uint8_t* p = static_cast<uint8_t*>(base);
+  size_t off = 0;
+  GptBuffers b;
+  b.h = reinterpret_cast<float*>(p + off);      off += align_up(R * w->dim * 4, 1024);
+  b.xn = p + off;                               off += align_up(R * w->dim * 2, 1024);
+  b.qkv = p + off;                              off += align_up(R * w->dim * 3 * 2, 1024);
+  b.att = p + off;                              off += align_up(R * w->dim * 2, 1024);
+  b.hid = p + off;                              off += align_up(R * w->dim * 4 * 2, 1024);
+  b.emb = reinterpret_cast<float*>(p + off);    off += align_up(R * w->dim * 4, 1024);
+  b.logits = reinterpret_cast<float*>(p + off); off += align_up(static_cast<size_t>(n_seq) * w->vocab_pad * 4, 1024);
+  b.finished = reinterpret_cast<int32_t*>(p + off); off += align_up(static_cast<size_t>(n_seq) * 4, 1024);
+  b.next = reinterpret_cast<int32_t*>(p + off);     off += align_up(static_cast<size_t>(n_seq) * 4, 1024);
+  b.total = off;
+  return b;
+}
+
+}  // namespace vc
+
+using namespace vc;
+
+extern "C" {
+
+const char* vc_last_error(void) { return g_err; }
+int vc_abi_version(void) { return 1; }
+int vc_num_sms(void) {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  return n;
+}
+long long vc_launch_count(void) { return g_launches.load(); }
+
+int vc_prof_begin(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  g_prof_on = true;
+  return 0;
+}
+int vc_prof_end(int max_rows, char* names, float* total_ms, int* calls, double* work) {
+  VC_CUDA_OK(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = false;
+  std::map<std::string, int> index;
+  int n = 0;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    auto it = index.find(r.name);
+    int i;
+    if (it == index.end()) {
+      if (n >= max_rows) continue;
+      i = n++;
+      index[r.name] = i;
+      std::snprintf(names + i * 48, 48, "%s", r.name);
+      total_ms[i] = 0.f; calls[i] = 0; work[i] = 0.0;
+    } else {
+      i = it->second;
+    }
+    total_ms[i] += ms; calls[i] += 1; work[i] += r.work;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  return n;
+}
+
+int vc_preprocess_u8(const uint8_t* frames_hwc, const float* lut3x256, void* out_bf16, int n_frames, int H, int W, int layout,
+                     int patch, int k_pad, vc_stream_t stream) {
+  return preprocess_u8(frames_hwc, lut3x256, out_bf16, n_frames, H, W, layout, patch, k_pad, S(stream));
+}
+
+int vc_gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int K, int epilogue, void* out, int ldo,
+                 const float* aux, int rows_per_group, vc_stream_t stream) {
+  return gemm_bf16(A, W, bias, M, N, K, epilogue, out, ldo, aux, rows_per_group, 0, S(stream));
+}
+
+int vc_layernorm_f32_bf16(const float* x, const float* gamma, const float* beta, void* out_bf16, int rows, int dim, float eps,
+                          vc_stream_t stream) {
+  return layernorm_f32_bf16(x, gamma, beta, out_bf16, rows, dim, eps, S(stream));
+}
+
+int vc_vit_attention(const void* qkv_bf16, void* out_bf16, int n_frames, int tokens, int heads, int head_dim, vc_stream_t stream) {
+  return vit_attention(qkv_bf16, out_bf16, n_frames, tokens, heads, head_dim, S(stream));
+}
+
+size_t vc_vit_workspace_bytes(const VcVitWeights* w, int chunk_frames) { return carve_vit(w, chunk_frames, nullptr).total; }
+
+int vc_vit_encode(const VcVitWeights* w, const void* patches_bf16, int n_frames, int chunk_frames, void* workspace,
+                  size_t workspace_bytes, float* cls_out, vc_stream_t stream) {
+  VC_REQUIRE(w != nullptr && w->layer != nullptr, "vit_encode: null weights");
+  VC_REQUIRE(chunk_frames > 0, "vit_encode: chunk_frames=%d", chunk_frames);
+  VC_REQUIRE(w->dim == w->heads * 64, "vit_encode: dim=%d heads=%d (head_dim must be 64)", w->dim, w->heads);
+  if (n_frames <= 0) return 0;
+  VitBuffers b = carve_vit(w, chunk_frames, workspace);
+  VC_REQUIRE(workspace != nullptr && workspace_bytes >= b.total, "vit_encode: workspace %zu < %zu bytes", workspace_bytes, b.total);
+  cudaStream_t s = S(stream);
+  const int D = w->dim, N = w->tokens, P = w->tokens - 1;
+  const int gelu = w->gelu_tanh ? VC_EPI_BIAS_GELU_TANH : VC_EPI_BIAS_GELU_ERF;
+  for (int f0 = 0; f0 < n_frames; f0 += chunk_frames) {
+    const int nf = (n_frames - f0 < chunk_frames) ? (n_frames - f0) : chunk_frames;
+    const int M = nf * N;
+    const __nv_bfloat16* patches = static_cast<const __nv_bfloat16*>(patches_bf16) + static_cast<size_t>(f0) * P * w->patch_k;
+    int e;
+    // tokens: [cls + pos0 | conv_proj(patches) + bias + pos]   (video_encoder.py:90-95, Encoder.forward)
+    if ((e = cls_rows_init(b.x, w->cls_pos0, nf, N, D, s))) return e;
+    if ((e = gemm_bf16(patches, w->patch_w, w->patch_b, nf * P, D, w->patch_k, VC_EPI_PATCH_EMBED, b.x, D, w->pos, P, 0, s))) return e;
+    for (int l = 0; l < w->layers; ++l) {
+      const VcVitLayer& L = w->layer[l];
+      if ((e = layernorm_f32_bf16(b.x, L.ln1_g, L.ln1_b, b.xn, M, D, 1e-6f, s))) return e;
+      if ((e = gemm_bf16(b.xn, L.qkv_w, L.qkv_b, M, 3 * D, D, VC_EPI_BIAS, b.qkv, 3 * D, nullptr, 0, 0, s))) return e;
+      if ((e = vit_attention(b.qkv, b.att, nf, N, w->heads, 64, s))) return e;
+      if ((e = gemm_bf16(b.att, L.proj_w, L.proj_b, M, D, D, VC_EPI_BIAS_RESID_F32, b.x, D, nullptr, 0, 0, s))) return e;
+      if ((e = layernorm_f32_bf16(b.x, L.ln2_g, L.ln2_b, b.xn, M, D, 1e-6f, s))) return e;
+      if ((e = gemm_bf16(b.xn, L.fc1_w, L.fc1_b, M, w->mlp, D, gelu, b.hid, w->mlp, nullptr, 0, 0, s))) return e;
+      if ((e = gemm_bf16(b.hid, L.fc2_w, L.fc2_b, M, D, w->mlp, VC_EPI_BIAS_RESID_F32, b.x, D, nullptr, 0, 0, s))) return e;
+    }
+    // only the class token of each frame is consumed downstream (video_encoder.py:256-258)
+    if ((e = layernorm_rows(b.x, N, 0, w->lnf_g, w->lnf_b, cls_out + static_cast<size_t>(f0) * D, nullptr, nf, D, 1e-6f, s))) return e;
+  }
+  return 0;
+}
+
+int vc_pool_prefix(const float* cls_tokens, int B, int T, int dim, const float* head_w, const float* head_b, int video_dim,
+                   float ln_scale, float in_weight, const float* mapper_w, const float* mapper_b, int mapper_out, float* feat_out,
+                   float* prefix_out, vc_stream_t stream) {
+  return pool_prefix(cls_tokens, B, T, dim, head_w, head_b, video_dim, ln_scale, in_weight, mapper_w, mapper_b, mapper_out, feat_out,
+                     prefix_out, S(stream));
+}
+int vc_vit_pool_temporal(const void* feat, int is_bf16, int bsz, int timesteps, int tokens, int channels, int gap, float* out,
+                         vc_stream_t stream) {
+  return vit_pool_temporal(feat, is_bf16, bsz, timesteps, tokens, channels, gap, out, S(stream));
+}
+int vc_linear_bias_f32(const float* x, const float* w, const float* b, float* y, int rows, int in_features, int out_features,
+                       vc_stream_t stream) {
+  return linear_bias_f32(x, w, b, y, rows, in_features, out_features, S(stream));
+}
+
+size_t vc_gpt_workspace_bytes(const VcGptWeights* w, int n_seq, int max_new_rows) { return carve_gpt(w, n_seq, max_new_rows, nullptr).total; }
+
+static int gpt_forward_impl(const VcGptWeights* w, const float* embeds, int n_seq, int L, int past_len, VcKvCache* cache,
+                            const GptBuffers& b, float* logits_out, cudaStream_t s) {
+  const int H = w->dim, M = n_seq * L;
+  int e;
+  if ((e = gpt_add_pos(embeds, w->wpe, b.h, n_seq, L, past_len, H, s))) return e;
+  for (int l = 0; l < w->layers; ++l) {
+    const VcGptLayer& Ly = w->layer[l];
+    if ((e = layernorm_f32_bf16(b.h, Ly.ln1_g, Ly.ln1_b, b.xn, M, H, 1e-5f, s))) return e;
+    if ((e = gemm_bf16(b.xn, Ly.attn_w, Ly.attn_b, M, 3 * H, H, VC_EPI_BIAS, b.qkv, 3 * H, nullptr, 0, 0, s))) return e;
+    if ((e = gpt_attention(b.qkv, b.att, cache, l, n_seq, L, past_len, s))) return e;
+    if ((e = gemm_bf16(b.att, Ly.aproj_w, Ly.aproj_b, M, H, H, VC_EPI_BIAS_RESID_F32, b.h, H, nullptr, 0, 0, s))) return e;
+    if ((e = layernorm_f32_bf16(b.h, Ly.ln2_g, Ly.ln2_b, b.xn, M, H, 1e-5f, s))) return e;
+    if ((e = gemm_bf16(b.xn, Ly.fc_w, Ly.fc_b, M, 4 * H, H, VC_EPI_BIAS_GELU_TANH, b.hid, 4 * H, nullptr, 0, 0, s))) return e;
+    if ((e = gemm_bf16(b.hid, Ly.mproj_w, Ly.mproj_b, M, H, 4 * H, VC_EPI_BIAS_RESID_F32, b.h, H, nullptr, 0, 0, s))) return e;
+  }
+  // ln_f + tied lm_head on the last position of every row only (HF computes all positions; unused)
+  if ((e = layernorm_rows(b.h, L, L - 1, w->lnf_g, w->lnf_b, nullptr, b.xn, n_seq, H, 1e-5f, s))) return e;
+  if ((e = gemm_bf16(b.xn, w->wte, nullptr, n_seq, w->vocab_pad, H, VC_EPI_BIAS_F32, logits_out, w->vocab_pad, nullptr, 0, 0, s))) return e;
+  return 0;
+}
+
+int vc_gpt2_forward(const VcGptWeights* w, const float* embeds, int n_seq, int L, int past_len, VcKvCache* cache, void* workspace,
+                    size_t workspace_bytes, float* logits_out, int32_t* next_ids, vc_stream_t stream) {
+  VC_REQUIRE(w != nullptr && w->layer != nullptr && cache != nullptr, "gpt2_forward: null argument");
+  VC_REQUIRE(n_seq > 0 && L > 0 && past_len >= 0, "gpt2_forward: n_seq=%d L=%d past_len=%d", n_seq, L, past_len);
+  VC_REQUIRE(past_len + L <= w->n_pos, "gpt2_forward: position %d exceeds n_positions=%d", past_len + L, w->n_pos);
+  GptBuffers b = carve_gpt(w, n_seq, n_seq * L, workspace);
+  VC_REQUIRE(workspace != nullptr && workspace_bytes >= b.total, "gpt2_forward: workspace %zu < %zu bytes", workspace_bytes, b.total);
+  float* lg = logits_out ? logits_out : b.logits;
+  int e = gpt_forward_impl(w, embeds, n_seq, L, past_len, cache, b, lg, S(stream));
+  if (e) return e;
+  if (next_ids) return argmax_f32(lg, w->vocab_pad, n_seq, w->vocab, next_ids, S(stream));
+  return 0;
+}
+
+int vc_gpt2_embed_tokens(const VcGptWeights* w, const int32_t* ids, int n, float* out, vc_stream_t stream) {
+  return embed_tokens(w->wte, ids, n, w->dim, out, S(stream));
+}
+
+int vc_greedy_decode(const VcGptWeights* w, const float* prefix, int n_seq, int P, const int32_t* prompt_ids, int Lp, int max_new,
+                     int eos, VcKvCache* cache, void* workspace, size_t workspace_bytes, int32_t* ids_out, int32_t* len_out,
+                     const int32_t* forced_ids, float* step_logits, vc_stream_t stream) {
+  VC_REQUIRE(w != nullptr && w->layer != nullptr && cache != nullptr, "greedy_decode: null argument");
+  VC_REQUIRE(n_seq > 0 && P >= 0 && Lp > 0 && max_new > 0, "greedy_decode: n_seq=%d P=%d Lp=%d max_new=%d", n_seq, P, Lp, max_new);
+  const int L0 = P + Lp;
+  VC_REQUIRE(L0 + max_new - 1 <= cache->s_max, "greedy_decode: %d positions exceed cache s_max=%d", L0 + max_new - 1, cache->s_max);
+  GptBuffers b = carve_gpt(w, n_seq, n_seq * L0, workspace);
+  VC_REQUIRE(workspace != nullptr && workspace_bytes >= b.total, "greedy_decode: workspace %zu < %zu bytes", workspace_bytes, b.total);
+  cudaStream_t s = S(stream);
+  int e;
+  if ((e = greedy_init(ids_out, len_out, b.finished, n_seq, max_new, eos, s))) return e;
+  if ((e = build_prefill_embeds(prefix, w->wte, prompt_ids, n_seq, P, Lp, w->dim, b.emb, s))) return e;
+  for (int step = 0; step < max_new; ++step) {
+    const int L = step == 0 ? L0 : 1;
+    const int past = step == 0 ? 0 : L0 + step - 1;
+    float* lg = step_logits ? step_logits + static_cast<size_t>(step) * n_seq * w->vocab_pad : b.logits;
+    if ((e = gpt_forward_impl(w, b.emb, n_seq, L, past, cache, b, lg, s))) return e;
+    const bool last = step == max_new - 1;
+    if ((e = greedy_select(lg, w->vocab_pad, w->vocab, n_seq, step, max_new, eos, b.finished, ids_out, len_out, forced_ids, w->wte,
+                           w->dim, last ? nullptr : b.emb, b.next, s)))
+      return e;
+  }
+  return 0;
+}
+
+int vc_argmax_f32(const float* logits, int rows, int vocab, int32_t* out, vc_stream_t stream) {
+  return argmax_f32(logits, vocab, rows, vocab, out, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,274 @@
+// GPT-2 decode-side kernels: position add, KV-cache attention (prefill and single-query
+// steps, with a per-position slot table so beam reorder never copies the cache), argmax /
+// greedy bookkeeping on device (no per-token host sync, unlike
+// core/scripts/benchmark_baseline.py:194-221), token embedding gather.
+// Arithmetic follows transformers GPT2Attention / GPT2Model.
+#include "vc_common.cuh"
+#include "vc_kernels.h"
+
+#include <algorithm>
+
+namespace vc {
+
+#define VC_LAUNCH(name, work, stream, ...)        \
+  do {                                            \
+    vc::KernelScope _ks(name, work, stream);      \
+    __VA_ARGS__;                                  \
+  } while (0)
+
+// h[s, l, :] = embeds[s, l, :] + wpe[past_len + l, :]     (GPT2Model.forward: inputs_embeds + position_embeds)
+__global__ void add_pos_kernel(const float* __restrict__ e, const float* __restrict__ wpe, float* __restrict__ h, int n_seq, int L,
+                               int past_len, int dim4) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(n_seq) * L * dim4;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % dim4);
+  const int l = static_cast<int>((i / dim4) % L);
+  const float4 a = reinterpret_cast<const float4*>(e)[i];
+  const float4 p = __ldg(reinterpret_cast<const float4*>(wpe) + static_cast<long long>(past_len + l) * dim4 + c);
+  reinterpret_cast<float4*>(h)[i] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+}
+int gpt_add_pos(const float* embeds, const float* wpe, float* h, int n_seq, int L, int past_len, int dim, cudaStream_t s) {
+  VC_REQUIRE(dim % 4 == 0, "add_pos: dim %% 4");
+  const long long total = static_cast<long long>(n_seq) * L * (dim / 4);
+  if (total == 0) return 0;
+  VC_LAUNCH("gpt_add_pos", total * 32.0, s,
+            (add_pos_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(embeds, wpe, h, n_seq, L, past_len, dim / 4)));
+  VC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ KV-cache attention
+// cache layout: kv[layer][k|v][seq][head][s_max][64] bf16.  slot[seq][pos] (optional) is the
+// physical seq row that holds position pos of logical row seq (beam search indirection).
+// One CTA per (seq, head): first appends the L new K/V rows, then each warp handles query
+// positions l = warp, warp+4, ...; lanes split the keys for the scores (one 128-byte row per
+// lane) and split head_dim for the weighted V sum (coalesced 128-byte rows).
+constexpr int GHD = 64;
+constexpr int ATT_MAX_S = 1024;   // GPT-2 n_positions
+
+__global__ void __launch_bounds__(128) gpt_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                                                            __nv_bfloat16* __restrict__ kv, const int32_t* __restrict__ slot,
+                                                            int layer, int n_seq, int heads, int s_max, int L, int past_len) {
+  __shared__ float s_p[4][ATT_MAX_S];
+  const int seq = blockIdx.x / heads, head = blockIdx.x - seq * heads;
+  const int H = heads * GHD;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long plane = static_cast<long long>(n_seq) * heads * s_max * GHD;        // one of K or V for one layer
+  __nv_bfloat16* kbase = kv + (static_cast<long long>(layer) * 2 + 0) * plane;
+  __nv_bfloat16* vbase = kv + (static_cast<long long>(layer) * 2 + 1) * plane;
+  const long long own = (static_cast<long long>(seq) * heads + head) * s_max * GHD;
+
+  // append new K/V rows (16-byte chunks: 8 per row)
+  for (int i = tid; i < L * 16; i += blockDim.x) {
+    const int l = i >> 4, which = (i >> 3) & 1, chunk = i & 7;
+    const uint4 v = *(reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(seq) * L + l) * 3 * H + (1 + which) * H + head * GHD) + chunk);
+    __nv_bfloat16* dst = (which ? vbase : kbase) + own + static_cast<long long>(past_len + l) * GHD;
+    reinterpret_cast<uint4*>(dst)[chunk] = v;
+  }
+  __syncthreads();
+
+  const float scale = 0.125f;   // head_dim^-0.5
+  for (int l = warp; l < L; l += 4) {
+    const int n_keys = past_len + l + 1;   // causal
+    // q in registers: every lane holds the full 64-dim query (bf16 pairs)
+    const uint4* qp = reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(seq) * L + l) * 3 * H + head * GHD);
+    float q[GHD];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = __ldg(qp + c);
+      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      q[c * 8 + 0] = a.x; q[c * 8 + 1] = a.y; q[c * 8 + 2] = b.x; q[c * 8 + 3] = b.y;
+      q[c * 8 + 4] = cc.x; q[c * 8 + 5] = cc.y; q[c * 8 + 6] = d.x; q[c * 8 + 7] = d.y;
+    }
+    float mx = -INFINITY;
+    for (int j = lane; j < n_keys; j += 32) {
+      const int phys = (slot != nullptr && j < past_len) ? slot[static_cast<long long>(seq) * s_max + j] : seq;
+      const uint4* kp = reinterpret_cast<const uint4*>(kbase + (static_cast<long long>(phys) * heads + head) * s_max * GHD + static_cast<long long>(j) * GHD);
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 u = kp[c];
+        const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+        acc = fmaf(q[c * 8 + 0], a.x, acc); acc = fmaf(q[c * 8 + 1], a.y, acc);
+        acc = fmaf(q[c * 8 + 2], b.x, acc); acc = fmaf(q[c * 8 + 3], b.y, acc);
+        acc = fmaf(q[c * 8 + 4], cc.x, acc); acc = fmaf(q[c * 8 + 5], cc.y, acc);
+        acc = fmaf(q[c * 8 + 6], d.x, acc); acc = fmaf(q[c * 8 + 7], d.y, acc);
+      }
+      acc *= scale;
+      s_p[warp][j] = acc;
+      mx = fmaxf(mx, acc);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < n_keys; j += 32) {
+      const float p = __expf(s_p[warp][j] - mx);
+      s_p[warp][j] = p;
+      sum += p;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < n_keys; ++j) {
+      const int phys = (slot != nullptr && j < past_len) ? slot[static_cast<long long>(seq) * s_max + j] : seq;
+      const uint32_t u = *(reinterpret_cast<const uint32_t*>(vbase + (static_cast<long long>(phys) * heads + head) * s_max * GHD + static_cast<long long>(j) * GHD) + lane);
+      const float2 v = unpack_bf16(u);
+      const float p = s_p[warp][j];
+      o0 = fmaf(p, v.x, o0);
+      o1 = fmaf(p, v.y, o1);
+    }
+    const float inv = 1.f / sum;
+    *(reinterpret_cast<uint32_t*>(out + (static_cast<long long>(seq) * L + l) * H + head * GHD) + lane) = pack_bf16(o0 * inv, o1 * inv);
+    __syncwarp();
+  }
+}
+
+int gpt_attention(const void* qkv, void* out, const VcKvCache* c, int layer, int n_seq, int L, int past_len, cudaStream_t s) {
+  VC_REQUIRE(c->head_dim == GHD, "gpt_attention: head_dim=%d (only 64 is built)", c->head_dim);
+  VC_REQUIRE(past_len + L <= c->s_max && c->s_max <= ATT_MAX_S, "gpt_attention: %d+%d positions exceed cache s_max=%d", past_len, L, c->s_max);
+  VC_REQUIRE(n_seq <= c->n_seq && layer < c->layers, "gpt_attention: cache too small");
+  if (n_seq <= 0 || L <= 0) return 0;
+  const double bytes = static_cast<double>(n_seq) * c->heads * GHD * 2.0 * (2.0 * L + 2.0 * (past_len + L));
+  VC_LAUNCH("gpt_attention", bytes, s,
+            (gpt_attention_kernel<<<n_seq * c->heads, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out),
+                                                                  static_cast<__nv_bfloat16*>(c->kv), c->slot, layer, c->n_seq, c->heads,
+                                                                  c->s_max, L, past_len)));
+  VC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ argmax (ties -> lowest index, torch.argmax)
+__device__ __forceinline__ void argmax_combine(float& v, int& i, float ov, int oi) {
+  if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+}
+__device__ int block_argmax(const float* __restrict__ row, int vocab) {
+  __shared__ float s_v[32];
+  __shared__ int s_i[32];
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = threadIdx.x; j < vocab; j += blockDim.x) {
+    const float v = row[j];
+    if (v > best || (v == best && j < bi)) { best = v; bi = j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    argmax_combine(best, bi, ov, oi);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (lane == 0) { s_v[warp] = best; s_i[warp] = bi; }
+  __syncthreads();
+  if (warp == 0) {
+    best = lane < nw ? s_v[lane] : -INFINITY;
+    bi = lane < nw ? s_i[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      argmax_combine(best, bi, ov, oi);
+    }
+    if (lane == 0) s_i[0] = (bi == 0x7fffffff) ? 0 : bi;
+  }
+  __syncthreads();
+  return s_i[0];
+}
+
+__global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, long long ld, int vocab, int32_t* __restrict__ out) {
+  const int r = blockIdx.x;
+  const int idx = block_argmax(logits + r * ld, vocab);
+  if (threadIdx.x == 0) out[r] = idx;
+}
+int argmax_f32(const float* logits, long long ld, int rows, int vocab, int32_t* out, cudaStream_t s) {
+  if (rows <= 0) return 0;
+  VC_REQUIRE(vocab > 0, "argmax: vocab=%d", vocab);
+  VC_LAUNCH("argmax", static_cast<double>(rows) * vocab * 4.0, s, (argmax_kernel<<<rows, 1024, 0, s>>>(logits, ld, vocab, out)));
+  VC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ embedding gather (wte bf16 -> fp32)
+__global__ void embed_kernel(const __nv_bfloat16* __restrict__ wte, const int32_t* __restrict__ ids, int dim, float* __restrict__ out) {
+  const int r = blockIdx.x;
+  const long long id = ids[r];
+  for (int c = threadIdx.x; c < dim; c += blockDim.x) out[static_cast<long long>(r) * dim + c] = __bfloat162float(wte[id * dim + c]);
+}
+int embed_tokens(const void* wte, const int32_t* ids, int n, int dim, float* out, cudaStream_t s) {
+  if (n <= 0) return 0;
+  VC_LAUNCH("embed_tokens", n * dim * 6.0, s, (embed_kernel<<<n, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(wte), ids, dim, out)));
+  VC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// inputs_embeds = cat([prefix, wte(prompt)], dim=1)   (text_decoder.py:60-74, benchmark_baseline.py:176-180)
+__global__ void prefill_embeds_kernel(const float* __restrict__ prefix, const __nv_bfloat16* __restrict__ wte,
+                                      const int32_t* __restrict__ prompt, int P, int Lp, int dim, float* __restrict__ out) {
+  const int s = blockIdx.x / (P + Lp), l = blockIdx.x - s * (P + Lp);
+  float* o = out + (static_cast<long long>(s) * (P + Lp) + l) * dim;
+  if (l < P) {
+    const float* src = prefix + (static_cast<long long>(s) * P + l) * dim;
+    for (int c = threadIdx.x; c < dim; c += blockDim.x) o[c] = src[c];
+  } else {
+    const long long id = prompt[l - P];
+    for (int c = threadIdx.x; c < dim; c += blockDim.x) o[c] = __bfloat162float(wte[id * dim + c]);
+  }
+}
+int build_prefill_embeds(const float* prefix, const void* wte, const int32_t* prompt_ids, int n_seq, int P, int Lp, int dim, float* out,
+                         cudaStream_t s) {
+  if (n_seq <= 0) return 0;
+  VC_LAUNCH("prefill_embeds", 0.0, s,
+            (prefill_embeds_kernel<<<n_seq * (P + Lp), 256, 0, s>>>(prefix, static_cast<const __nv_bfloat16*>(wte), prompt_ids, P, Lp, dim, out)));
+  VC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ greedy bookkeeping
+__global__ void greedy_init_kernel(int32_t* ids_out, int32_t* len_out, int32_t* finished, int n_seq, int max_new, int eos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_seq * max_new) ids_out[i] = eos;
+  if (i < n_seq) { len_out[i] = 0; finished[i] = 0; }
+}
+int greedy_init(int32_t* ids_out, int32_t* len_out, int32_t* finished, int n_seq, int max_new, int eos, cudaStream_t s) {
+  const int total = std::max(n_seq * max_new, n_seq);
+  if (total <= 0) return 0;
+  VC_LAUNCH("greedy_init", 0.0, s, (greedy_init_kernel<<<(total + 255) / 256, 256, 0, s>>>(ids_out, len_out, finished, n_seq, max_new, eos)));
+  VC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// benchmark_baseline.py:210-227: next = argmax(logits[:, -1]); finished rows -> eos; unfinished rows
+// append the token (including their first eos) and become finished on eos; next input = wte(next).
+__global__ void __launch_bounds__(1024) greedy_select_kernel(const float* __restrict__ logits, long long ld, int vocab, int step, int max_new,
+                                                             int eos, int32_t* __restrict__ finished, int32_t* __restrict__ ids_out,
+                                                             int32_t* __restrict__ len_out, const int32_t* __restrict__ forced,
+                                                             const __nv_bfloat16* __restrict__ wte, int dim, float* __restrict__ next_embeds,
+                                                             int32_t* __restrict__ next_ids) {
+  const int r = blockIdx.x;
+  int tok = block_argmax(logits + r * ld, vocab);
+  const bool was_finished = finished[r] != 0;
+  if (was_finished) tok = eos;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (!was_finished) {
+      ids_out[static_cast<long long>(r) * max_new + step] = tok;
+      len_out[r] += 1;
+      if (tok == eos) finished[r] = 1;
+    }
+    if (next_ids != nullptr) next_ids[r] = tok;
+  }
+  const long long feed = (forced != nullptr) ? forced[static_cast<long long>(r) * max_new + step] : tok;
+  if (next_embeds != nullptr)
+    for (int c = threadIdx.x; c < dim; c += blockDim.x) next_embeds[static_cast<long long>(r) * dim + c] = __bfloat162float(wte[feed * dim + c]);
+}
+int greedy_select(const float* logits, long long ld, int vocab, int n_seq, int step, int max_new, int eos, int32_t* finished,
+                  int32_t* ids_out, int32_t* len_out, const int32_t* forced, const void* wte, int dim, float* next_embeds,
+                  int32_t* next_ids, cudaStream_t s) {
+  if (n_seq <= 0) return 0;
+  VC_LAUNCH("greedy_select", static_cast<double>(n_seq) * vocab * 4.0, s,
+            (greedy_select_kernel<<<n_seq, 1024, 0, s>>>(logits, ld, vocab, step, max_new, eos, finished, ids_out, len_out, forced,
+                                                         static_cast<const __nv_bfloat16*>(wte), dim, next_embeds, next_ids)));
+  VC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vc

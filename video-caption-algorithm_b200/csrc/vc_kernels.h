@@ -1,0 +1,56 @@
+// Internal host-side declarations shared by the .cu translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/vcb200.h"
+
+namespace vc {
+
+void set_error(const char* fmt, ...);
+
+// Counts every kernel launch (bench.py "gpu_launches") and, while profiling is on,
+// brackets it with CUDA events on the launch stream.
+struct KernelScope {
+  KernelScope(const char* name, double work, cudaStream_t stream);
+  ~KernelScope();
+  cudaStream_t stream_;
+  int slot_;
+};
+
+// gemm_tcgen05.cu
+int gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int K, int mode, void* out, int ldo,
+              const float* aux, int rows_per_group, int max_ctas, cudaStream_t stream);
+
+// vit_kernels.cu
+int preprocess_u8(const uint8_t* frames, const float* lut, void* out, int n, int H, int W, int layout, int patch, int k_pad,
+                  cudaStream_t s);
+int layernorm_f32_bf16(const float* x, const float* g, const float* b, void* out, int rows, int dim, float eps,
+                       cudaStream_t s);
+// fp32 rows picked with a stride (class tokens / last positions): out = LN(x[r*row_stride + row_offset])
+int layernorm_rows(const float* x, long long row_stride, long long row_offset, const float* g, const float* b, float* out_f32,
+                   void* out_bf16, int rows, int dim, float eps, cudaStream_t s);
+int vit_attention(const void* qkv, void* out, int n_frames, int tokens, int heads, int head_dim, cudaStream_t s);
+int cls_rows_init(float* x, const float* cls_pos0, int n_frames, int tokens, int dim, cudaStream_t s);
+int pool_prefix(const float* cls, int B, int T, int dim, const float* head_w, const float* head_b, int video_dim,
+                float ln_scale, float in_weight, const float* mapper_w, const float* mapper_b, int mapper_out,
+                float* feat_out, float* prefix_out, cudaStream_t s);
+int vit_pool_temporal(const void* feat, int is_bf16, int bsz, int T, int tokens, int C, int gap, float* out, cudaStream_t s);
+int linear_bias_f32(const float* x, const float* w, const float* b, float* y, int rows, int in_f, int out_f, cudaStream_t s);
+
+// gpt2_kernels.cu
+int gpt_add_pos(const float* embeds, const float* wpe, float* h, int n_seq, int L, int past_len, int dim, cudaStream_t s);
+int gpt_attention(const void* qkv, void* out, const VcKvCache* cache, int layer, int n_seq, int L, int past_len,
+                  cudaStream_t s);
+int argmax_f32(const float* logits, long long ld, int rows, int vocab, int32_t* out, cudaStream_t s);
+int embed_tokens(const void* wte_bf16, const int32_t* ids, int n, int dim, float* out, cudaStream_t s);
+int greedy_init(int32_t* ids_out, int32_t* len_out, int32_t* finished, int n_seq, int max_new, int eos, cudaStream_t s);
+// argmax of logits rows + the bookkeeping of benchmark_baseline.py:210-227 + wte gather for the next step
+int greedy_select(const float* logits, long long ld, int vocab, int n_seq, int step, int max_new, int eos, int32_t* finished,
+                  int32_t* ids_out, int32_t* len_out, const int32_t* forced, const void* wte_bf16, int dim, float* next_embeds,
+                  int32_t* next_ids, cudaStream_t s);
+int build_prefill_embeds(const float* prefix, const void* wte_bf16, const int32_t* prompt_ids, int n_seq, int P, int Lp,
+                         int dim, float* out, cudaStream_t s);
+
+}  // namespace vc
