@@ -1,0 +1,234 @@
+"""Per-kernel parity on the B200 through the C ABI (ctypes), against fp32 torch references
+and the CPU oracle.  Integer / byte / index work must be bit-exact; floating point states
+its tolerance next to the assert."""
+import ctypes as C
+
+import pytest
+import torch
+
+import vcb200  # noqa: F401
+from vcb200 import lib as L
+from oracle import vc_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return L.load()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ------------------------------------------------------------------ preprocessing (bit-exact)
+@pytest.mark.parametrize("n,size", [(1, 224), (5, 224), (0, 224)])
+def test_preprocess_chw_bit_exact(lib, n, size):
+    g = torch.Generator().manual_seed(7)
+    frames = torch.randint(0, 256, (n, size, size, 3), generator=g, dtype=torch.uint8)
+    ref = O.preprocess_u8(frames).to(torch.bfloat16)          # reference tensor, bf16-rounded
+    lut = O.normalize_lut().to(DEV)
+    out = torch.empty(n, 3, size, size, device=DEV, dtype=torch.bfloat16)
+    L.check(lib.vc_preprocess_u8(frames.to(DEV).data_ptr(), lut.data_ptr(), out.data_ptr(), n, size, size, 0, 16, 768, _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), ref)
+
+
+@pytest.mark.parametrize("patch,k_pad", [(16, 768), (14, 640)])
+def test_preprocess_patch_major_is_a_permutation_of_chw(lib, patch, k_pad):
+    n, size = 3, 224
+    g = torch.Generator().manual_seed(11)
+    frames = torch.randint(0, 256, (n, size, size, 3), generator=g, dtype=torch.uint8)
+    ref = O.preprocess_u8(frames).to(torch.bfloat16)          # [n,3,H,W]
+    gsz = size // patch
+    # im2col of the reference tensor: rows (frame, py, px), columns (c, i, j) — Conv2d weight order
+    cols = ref.view(n, 3, gsz, patch, gsz, patch).permute(0, 2, 4, 1, 3, 5).reshape(n * gsz * gsz, 3 * patch * patch)
+    lut = O.normalize_lut().to(DEV)
+    out = torch.full((n * gsz * gsz, k_pad), 7.0, device=DEV, dtype=torch.bfloat16)
+    L.check(lib.vc_preprocess_u8(frames.to(DEV).data_ptr(), lut.data_ptr(), out.data_ptr(), n, size, size, 1, patch, k_pad, _stream()))
+    torch.cuda.synchronize()
+    out = out.cpu()
+    assert torch.equal(out[:, : 3 * patch * patch], cols)
+    assert bool((out[:, 3 * patch * patch:] == 0).all())      # K padding is zero
+
+
+def test_patchify_f32_matches_preprocess(lib):
+    n, size = 2, 224
+    frames = torch.randint(0, 256, (n, size, size, 3), dtype=torch.uint8)
+    video = O.preprocess_u8(frames)
+    a = torch.empty(n * 196, 768, device=DEV, dtype=torch.bfloat16)
+    b = torch.empty_like(a)
+    lut = O.normalize_lut().to(DEV)
+    L.check(lib.vc_preprocess_u8(frames.to(DEV).data_ptr(), lut.data_ptr(), a.data_ptr(), n, size, size, 1, 16, 768, _stream()))
+    L.check(lib.vc_patchify_f32(video.to(DEV).data_ptr(), b.data_ptr(), n, size, size, 16, 768, _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------ tcgen05 GEMM
+def _gemm_ref(A, W, bias):
+    return A.float() @ W.float().t() + (bias if bias is not None else 0.0)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 768), (197, 768, 768), (1000, 2304, 768), (64, 768, 3072),
+                                   (333, 3072, 768), (5, 256, 128), (4096, 768, 3072)])
+def test_gemm_bias_bf16(lib, M, N, K):
+    torch.manual_seed(M + N + K)
+    A = (torch.randn(M, K, device=DEV) * 0.5).to(torch.bfloat16)
+    W = (torch.randn(N, K, device=DEV) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, device=DEV)
+    out = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    L.check(lib.vc_gemm_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), M, N, K, 0, out.data_ptr(), N, 0, 0, _stream()))
+    torch.cuda.synchronize()
+    ref = _gemm_ref(A, W, bias)
+    err = (out.float() - ref).abs().max().item()
+    # fp32 accumulate of bf16 products, output rounded to bf16: |ref| <~ 8 -> half-ulp 2^-6 plus accumulation noise
+    assert err < 0.05, err
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_gemm_gelu_epilogues(lib, mode):
+    M, N, K = 300, 512, 256
+    torch.manual_seed(mode)
+    A = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+    W = (torch.randn(N, K, device=DEV) * 0.1).to(torch.bfloat16)
+    bias = torch.randn(N, device=DEV) * 0.1
+    out = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    L.check(lib.vc_gemm_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), M, N, K, mode, out.data_ptr(), N, 0, 0, _stream()))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.gelu(_gemm_ref(A, W, bias), approximate="tanh" if mode == 2 else "none")
+    assert (out.float() - ref).abs().max().item() < 0.03      # bf16 output rounding of |y| < 8
+
+
+def test_gemm_residual_and_f32_epilogues(lib):
+    M, N, K = 257, 768, 3072
+    torch.manual_seed(3)
+    A = (torch.randn(M, K, device=DEV) * 0.3).to(torch.bfloat16)
+    W = (torch.randn(N, K, device=DEV) * 0.02).to(torch.bfloat16)
+    bias = torch.randn(N, device=DEV)
+    res = torch.randn(M, N, device=DEV)
+    ref = res + _gemm_ref(A, W, bias)
+    L.check(lib.vc_gemm_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), M, N, K, 3, res.data_ptr(), N, 0, 0, _stream()))
+    out32 = torch.zeros(M, N, device=DEV)
+    L.check(lib.vc_gemm_bf16(A.data_ptr(), W.data_ptr(), 0, M, N, K, 4, out32.data_ptr(), N, 0, 0, _stream()))
+    torch.cuda.synchronize()
+    assert (res - ref).abs().max().item() < 2e-3               # fp32 out: only accumulation-order noise
+    assert (out32 - _gemm_ref(A, W, None)).abs().max().item() < 2e-3
+
+
+def test_gemm_patch_embed_epilogue(lib):
+    frames, P, D, K = 3, 196, 768, 768
+    M = frames * P
+    torch.manual_seed(5)
+    A = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+    W = (torch.randn(D, K, device=DEV) * 0.03).to(torch.bfloat16)
+    bias = torch.randn(D, device=DEV)
+    pos = torch.randn(P + 1, D, device=DEV)
+    x = torch.full((frames * (P + 1), D), -5.0, device=DEV)
+    L.check(lib.vc_gemm_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), M, D, K, 5, x.data_ptr(), D, pos.data_ptr(), P, _stream()))
+    torch.cuda.synchronize()
+    ref = (_gemm_ref(A, W, bias).view(frames, P, D) + pos[1:].unsqueeze(0))
+    got = x.view(frames, P + 1, D)
+    assert (got[:, 1:] - ref).abs().max().item() < 2e-3
+    assert bool((got[:, 0] == -5.0).all())                     # class-token rows untouched
+
+
+def test_gemm_rejects_bad_k(lib):
+    A = torch.zeros(8, 40, device=DEV, dtype=torch.bfloat16)
+    W = torch.zeros(32, 40, device=DEV, dtype=torch.bfloat16)
+    out = torch.zeros(8, 32, device=DEV, dtype=torch.bfloat16)
+    rc = lib.vc_gemm_bf16(A.data_ptr(), W.data_ptr(), 0, 8, 32, 40, 0, out.data_ptr(), 32, 0, 0, _stream())
+    assert rc != 0 and b"multiple of 64" in lib.vc_last_error()
+
+
+# ------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("rows,dim,eps", [(1, 768, 1e-6), (197 * 3, 768, 1e-6), (64, 1024, 1e-5)])
+def test_layernorm(lib, rows, dim, eps):
+    torch.manual_seed(rows)
+    x = torch.randn(rows, dim, device=DEV) * 2 + 0.3
+    g = torch.randn(dim, device=DEV) * 0.1 + 1
+    b = torch.randn(dim, device=DEV) * 0.05
+    out = torch.empty(rows, dim, device=DEV, dtype=torch.bfloat16)
+    L.check(lib.vc_layernorm_f32_bf16(x.data_ptr(), g.data_ptr(), b.data_ptr(), out.data_ptr(), rows, dim, eps, _stream()))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x, (dim,), g, b, eps)
+    assert (out.float() - ref).abs().max().item() < 0.04       # bf16 rounding of |y| < 8
+
+
+# ------------------------------------------------------------------ ViT attention
+@pytest.mark.parametrize("frames,tokens,heads", [(1, 197, 12), (3, 197, 12), (2, 257, 16), (2, 50, 2), (1, 64, 1)])
+def test_vit_attention(lib, frames, tokens, heads):
+    D = heads * 64
+    torch.manual_seed(tokens)
+    qkv = torch.randn(frames * tokens, 3 * D, device=DEV).to(torch.bfloat16)
+    out = torch.zeros(frames * tokens, D, device=DEV, dtype=torch.bfloat16)
+    L.check(lib.vc_vit_attention(qkv.data_ptr(), out.data_ptr(), frames, tokens, heads, 64, _stream()))
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().view(frames, tokens, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v
+    ref = ref.transpose(1, 2).reshape(frames * tokens, D)
+    assert (out.float() - ref).abs().max().item() < 0.03       # P rounded to bf16 before PV + bf16 output
+
+
+# ------------------------------------------------------------------ pool / prefix and the two CuPy-hook operators
+def test_pool_prefix_matches_oracle(lib):
+    B, T, D, Vd, Pn, H = 3, 4, 768, 256, 4, 768
+    torch.manual_seed(1)
+    cls = torch.randn(B * T, D)
+    sd = {"encoder.proj.weight": torch.randn(Vd, D) * 0.02, "encoder.proj.bias": torch.randn(Vd) * 0.02,
+          "decoder.mapper.0.weight": torch.randn(Pn * H, Vd) * 0.03, "decoder.mapper.0.bias": torch.randn(Pn * H) * 0.02}
+    feat_ref = torch.nn.functional.linear(cls.view(B, T, D).mean(1), sd["encoder.proj.weight"], sd["encoder.proj.bias"])
+    prefix_ref = O.visual_prefix(sd, feat_ref, 0.6, 0.4, Pn)
+    d = {k: v.to(DEV) for k, v in sd.items()}
+    feat = torch.empty(B, Vd, device=DEV)
+    prefix = torch.empty(B, Pn * H, device=DEV)
+    L.check(lib.vc_pool_prefix(cls.to(DEV).data_ptr(), B, T, D, d["encoder.proj.weight"].data_ptr(), d["encoder.proj.bias"].data_ptr(),
+                               Vd, 0.6, 0.4, d["decoder.mapper.0.weight"].data_ptr(), d["decoder.mapper.0.bias"].data_ptr(), Pn * H,
+                               feat.data_ptr(), prefix.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    assert (feat.cpu() - feat_ref).abs().max().item() < 1e-5   # fp32 throughout, summation order only
+    assert (prefix.cpu().view(B, Pn, H) - prefix_ref).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("gap", [0, 1])
+def test_vit_pool_temporal_hook(lib, gap):
+    """Same contract as core/operators/cupy_vit_pool.py:127-186 (cls / gap)."""
+    bsz, T, N, Cc = 2, 3, 17, 96
+    feat = torch.randn(bsz * T, N, Cc, device=DEV)
+    out = torch.empty(bsz, Cc, device=DEV)
+    L.check(lib.vc_vit_pool_temporal(feat.data_ptr(), 0, bsz, T, N, Cc, gap, out.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    f = feat.view(bsz, T, N, Cc)
+    ref = f[:, :, 1:, :].mean(dim=(1, 2)) if gap else f[:, :, 0, :].mean(dim=1)
+    assert (out - ref).abs().max().item() < 1e-5
+
+
+def test_linear_bias_hook(lib):
+    """Same contract as cupy_linear_mapper.py `linear_bias_f32` (:14-40)."""
+    x = torch.randn(5, 256, device=DEV)
+    w = torch.randn(3072, 256, device=DEV) * 0.05
+    b = torch.randn(3072, device=DEV)
+    y = torch.empty(5, 3072, device=DEV)
+    L.check(lib.vc_linear_bias_f32(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), 5, 256, 3072, _stream()))
+    torch.cuda.synchronize()
+    assert (y - torch.nn.functional.linear(x, w, b)).abs().max().item() < 1e-4
+
+
+# ------------------------------------------------------------------ token selection (bit-exact)
+def test_argmax_bit_exact_with_ties(lib):
+    torch.manual_seed(0)
+    rows, V = 37, 50257
+    logits = torch.randn(rows, V)
+    logits[3, 100] = logits[3, 40000] = 9.0                   # tie -> lowest index
+    logits[5, :] = -1.5                                        # all equal -> index 0
+    logits[7, V - 1] = 50.0
+    out = torch.empty(rows, device=DEV, dtype=torch.int32)
+    L.check(lib.vc_argmax_f32(logits.to(DEV).data_ptr(), rows, V, out.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    assert out.cpu().tolist() == torch.argmax(logits, dim=-1).tolist()
+    assert out[3].item() == 100 and out[5].item() == 0 and out[7].item() == V - 1

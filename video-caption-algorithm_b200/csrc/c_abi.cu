@@ -148,9 +148,17 @@ int vc_preprocess_u8(const uint8_t* frames_hwc, const float* lut3x256, void* out
   return preprocess_u8(frames_hwc, lut3x256, out_bf16, n_frames, H, W, layout, patch, k_pad, S(stream));
 }
 
+int vc_patchify_f32(const float* video_chw, void* out_bf16, int n_frames, int H, int W, int patch, int k_pad, vc_stream_t stream) {
+  return patchify_f32(video_chw, out_bf16, n_frames, H, W, patch, k_pad, S(stream));
+}
+
 int vc_gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int K, int epilogue, void* out, int ldo,
                  const float* aux, int rows_per_group, vc_stream_t stream) {
   return gemm_bf16(A, W, bias, M, N, K, epilogue, out, ldo, aux, rows_per_group, 0, S(stream));
+}
+
+void vc_debug_gemm_override(unsigned long long desc_hi, unsigned int k_adv, unsigned int idesc) {
+  gemm_debug_override(desc_hi, k_adv, idesc);
 }
 
 int vc_layernorm_f32_bf16(const float* x, const float* gamma, const float* beta, void* out_bf16, int rows, int dim, float eps,

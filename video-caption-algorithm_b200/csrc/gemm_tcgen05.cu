@@ -41,6 +41,9 @@ struct GemmParams {
   int ldo;                // leading dimension of out (elements)
   const float* aux;       // patch-embed: pos embedding [tokens, N]
   int rows_per_group;     // patch-embed: patches per frame (196); out row = g*(rpg+1)+1+r
+  uint64_t desc_hi;       // smem descriptor without the start address (see umma_desc_sw128)
+  uint32_t k_adv;         // start-address step per K=16 slice, in 16-byte units
+  uint32_t idesc;         // tcgen05 instruction descriptor
 };
 
 template <int MODE>
@@ -150,7 +153,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer (one lane)
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      const uint32_t idesc = p.idesc;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
@@ -161,12 +164,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t da = umma_desc_sw128(a_addr);
-          const uint64_t db = umma_desc_sw128(a_addr + A_BYTES);
+          const uint64_t da = p.desc_hi | static_cast<uint64_t>((a_addr & 0x3FFFFu) >> 4);
+          const uint64_t db = p.desc_hi | static_cast<uint64_t>(((a_addr + A_BYTES) & 0x3FFFFu) >> 4);
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             // +32 B per K=16 slice inside the 128 B swizzle row (start address is in 16 B units)
-            tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            tc_mma_bf16(d_tmem, da + p.k_adv * k, db + p.k_adv * k, idesc, (kb | k) != 0);
           }
           tc_commit(&empty_bar[stage]);            // smem slot reusable once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -243,6 +246,9 @@ int make_map(CUtensorMap* tm, const void* ptr, int rows, int K, int box_rows) {
 }
 
 int g_num_sms = 0;
+// bring-up overrides (vc_debug_gemm_override); 0 = built-in encoding
+uint64_t g_dbg_desc_hi = 0;
+uint32_t g_dbg_k_adv = 0, g_dbg_idesc = 0;
 std::mutex g_cfg_mu;
 bool g_attr_set[8] = {false};
 
@@ -262,6 +268,10 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
 
 }  // namespace
 
+void gemm_debug_override(uint64_t desc_hi, uint32_t k_adv, uint32_t idesc) {
+  g_dbg_desc_hi = desc_hi; g_dbg_k_adv = k_adv; g_dbg_idesc = idesc;
+}
+
 int gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int K, int mode, void* out, int ldo,
               const float* aux, int rows_per_group, int max_ctas, cudaStream_t stream) {
   VC_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
@@ -279,7 +289,10 @@ int gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int
   CUtensorMap ta, tb;
   if (int e = make_map(&ta, A, M, K, BM)) return e;
   if (int e = make_map(&tb, W, N, K, BN)) return e;
-  GemmParams p{M, N, K, mode, bias, out, ldo, aux, rows_per_group};
+  GemmParams p{M, N, K, mode, bias, out, ldo, aux, rows_per_group,
+               g_dbg_desc_hi ? g_dbg_desc_hi : umma_desc_sw128_hi(),
+               g_dbg_k_adv ? g_dbg_k_adv : 2u,
+               g_dbg_idesc ? g_dbg_idesc : umma_idesc_bf16(BM, BN)};
   const int total = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   int grid = total < g_num_sms ? total : g_num_sms;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;

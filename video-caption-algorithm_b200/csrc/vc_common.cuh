@@ -159,14 +159,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) |
 //   [32,46) SBO>>4 = 1024 B between 8-row groups | [46,48) version 1 (sm_100) |
 //   [61,64) layout 2 = SWIZZLE_128B.
+__host__ __device__ constexpr uint64_t umma_desc_sw128_hi() {
+  return (static_cast<uint64_t>(1) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) |
+         (static_cast<uint64_t>(2) << 61);
+}
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
+  return umma_desc_sw128_hi() | static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
 }
 // Instruction descriptor, kind::f16: D fp32 (bit 4), A/B bf16 (bits 7,10), both K-major,
 // N>>3 at [17,23), M>>4 at [24,29).

@@ -23,9 +23,12 @@ struct KernelScope {
 int gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int K, int mode, void* out, int ldo,
               const float* aux, int rows_per_group, int max_ctas, cudaStream_t stream);
 
+void gemm_debug_override(uint64_t desc_hi, uint32_t k_adv, uint32_t idesc);
+
 // vit_kernels.cu
 int preprocess_u8(const uint8_t* frames, const float* lut, void* out, int n, int H, int W, int layout, int patch, int k_pad,
                   cudaStream_t s);
+int patchify_f32(const float* video, void* out, int n, int H, int W, int patch, int k_pad, cudaStream_t s);
 int layernorm_f32_bf16(const float* x, const float* g, const float* b, void* out, int rows, int dim, float eps,
                        cudaStream_t s);
 // fp32 rows picked with a stride (class tokens / last positions): out = LN(x[r*row_stride + row_offset])

@@ -81,6 +81,41 @@ __global__ void __launch_bounds__(256) preprocess_generic_kernel(const uint8_t* 
   }
 }
 
+// fp32 [n,3,H,W] (the reference's normalised tensor, frame_loader.py:47) -> bf16 patch-major rows.
+// Lets `model.encoder(video)` accept exactly what core/engine.py:43 passes.
+__global__ void __launch_bounds__(256) patchify_f32_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int n_frames,
+                                                           int H, int W, int patch, int k_pad) {
+  const long long total = static_cast<long long>(n_frames) * 3 * H * W;
+  const int gw = W / patch, gh = H / patch;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(idx % W);
+    long long r = idx / W;
+    const int y = static_cast<int>(r % H);
+    r /= H;
+    const int c = static_cast<int>(r % 3);
+    const long long f = r / 3;
+    const int py = y / patch, i = y - py * patch, px = x / patch, j = x - px * patch;
+    out[((f * gh + py) * gw + px) * static_cast<long long>(k_pad) + (c * patch + i) * patch + j] = __float2bfloat16_rn(in[idx]);
+  }
+}
+
+int patchify_f32(const float* video, void* out, int n, int H, int W, int patch, int k_pad, cudaStream_t s) {
+  VC_REQUIRE(n >= 0 && patch > 0 && H % patch == 0 && W % patch == 0, "patchify: bad shape n=%d H=%d W=%d patch=%d", n, H, W, patch);
+  VC_REQUIRE(k_pad >= 3 * patch * patch, "patchify: k_pad=%d too small", k_pad);
+  if (n == 0) return 0;
+  if (k_pad != 3 * patch * patch) {
+    const size_t rows = static_cast<size_t>(n) * (H / patch) * (W / patch);
+    VC_CUDA_OK(cudaMemsetAsync(out, 0, rows * k_pad * 2, s));
+  }
+  const long long total = static_cast<long long>(n) * 3 * H * W;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
+  VC_LAUNCH("patchify_f32", static_cast<double>(total) * 6.0, s,
+            (patchify_f32_kernel<<<grid, 256, 0, s>>>(video, static_cast<__nv_bfloat16*>(out), n, H, W, patch, k_pad)));
+  VC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int preprocess_u8(const uint8_t* frames, const float* lut, void* out, int n, int H, int W, int layout, int patch, int k_pad,
                   cudaStream_t s) {
   VC_REQUIRE(n >= 0 && H > 0 && W > 0, "preprocess: bad shape n=%d H=%d W=%d", n, H, W);
