@@ -1,0 +1,335 @@
+"""bench.py — captions/sec of the video-caption hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm  (torchrun for N>1)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+
+A "step" is one pass of the hot path over one batch of synthetic input:
+uint8 frames -> preprocess -> ViT-B/16 over B*T frames -> pool/prefix -> GPT-2 small greedy
+decode of 20 tokens -> token ids (configs[1] of BASELINE.json: 64 videos x 16 frames per GPU;
+random-init weights of that architecture, synthetic structured frames).  N>1 shards by video
+(64 per GPU, weak scaling) and gathers the ids with one NCCL all_gather.
+
+`value`   : whole-job captions/s with the uint8 frames already resident in HBM.
+`e2e`     : the same through the public host-buffer call (pinned uint8 frames H2D + ids D2H
+            inside the timed region).
+`roofline`: the tcgen05 GEMM kernel (tensor bound), achieved TFLOP/s over its launches in one
+            encoder pass timed live with CUDA events on the launch stream, vs the measured
+            sustained bf16 peak; `decode` carries the HBM-bound decode-step figures.
+`cpu_baseline`: oracle port (torch CPU fp32 restatement of the reference) on the host cores,
+            on a bounded sample (1 video x 16 frames x 20 tokens per iteration).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+ARCH = "vit_b16_gpt2"
+VIT_GFLOP_PER_FRAME = 35.126120448          # 2 x 17,563,060,224 MAC
+GPT_WEIGHT_BYTES = 247_306_752              # GPT-2 small bf16 weights + biases + LN
+KV_BYTES_PER_TOKEN = 36_864
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="videos per GPU")
+    ap.add_argument("--frames", type=int, default=16)
+    ap.add_argument("--max-new", type=int, default=20)
+    ap.add_argument("--chunk-frames", type=int, default=int(os.environ.get("VC_CHUNK_FRAMES", "256")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+# --------------------------------------------------------------------------- CPU arm
+def cpu_sample(iters: int, warmup: int, frames: int, max_new: int):
+    """The reference's CPU path restated by the oracle, on a bounded sample of the workload."""
+    import torch
+    import vcb200  # noqa: F401
+    from vcb200 import synthetic
+    from oracle import vc_oracle as O
+
+    a = synthetic.ARCHS[ARCH]
+    sd = synthetic.make_state_dict(a, seed=1234)
+    video = synthetic.make_batch_u8(0, 1, frames)
+    times, enc_ms, step_ms = [], [], []
+    with torch.inference_mode():
+        for it in range(warmup + iters):
+            t0 = time.perf_counter()
+            v = O.preprocess_u8(video)
+            feat = O.encode(sd, v, a.vit_heads)
+            t1 = time.perf_counter()
+            prefix = O.visual_prefix(sd, feat)
+            ids, lens, _ = O.greedy_decode(sd, prefix, torch.tensor([[50256]]), max_new, heads=a.gpt_heads,
+                                           forced_ids=torch.zeros(1, max_new, dtype=torch.int64) + 11)   # never stops early
+            t2 = time.perf_counter()
+            if it >= warmup:
+                times.append(t2 - t0)
+                enc_ms.append((t1 - t0) * 1e3)
+                step_ms.append((t2 - t1) * 1e3 / max_new)
+    per = statistics.mean(times)
+    return dict(value=1.0 / per, unit="captions/s", cores=torch.get_num_threads(), kind="port",
+                sample=f"{iters} iters of 1 video x {frames} frames 224x224, {max_new} greedy tokens, fp32, oracle port "
+                       f"(ViT {statistics.mean(enc_ms):.0f} ms, decode step {statistics.mean(step_ms):.1f} ms)",
+                host_cpus=os.cpu_count()), per
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, per = cpu_sample(max(args.steps, 1), max(args.warmup, 1), args.frames, args.max_new)
+    line = {
+        "impl": "reference", "metric": "captions/sec (16-frame clips)", "value": base["value"], "unit": "captions/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"ViT-B/16 + GPT-2 small, {args.frames} frames 224x224 per video, greedy {args.max_new} tokens; "
+                               "each step = 1 video on the host CPU (bounded sample of the batch-64 workload)"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- our arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import vcb200  # noqa: F401
+    from vcb200 import lib as L
+    from vcb200 import synthetic
+    from vcb200.model import B200CaptionModel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the b200 arm has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.load()
+    a = synthetic.ARCHS[ARCH]
+    B, T, n_new = args.batch, args.frames, args.max_new
+    sd = synthetic.make_state_dict(a, seed=1234)
+    model = B200CaptionModel(sd, dev, vit_heads=a.vit_heads, gpt_heads=a.gpt_heads, chunk_frames=args.chunk_frames)
+    del sd
+    # this rank's shard: global video indices rank*B .. rank*B+B-1 (reproducible for any world size)
+    host_frames = synthetic.make_batch_u8(rank * B, B, T).pin_memory()
+    dev_frames = host_frames.to(dev)
+    gathered = [torch.empty(B, n_new, device=dev, dtype=torch.int32) for _ in range(world)] if world > 1 else None
+
+    def step_resident():
+        ids, lens = model.caption_ids(dev_frames, max_new_tokens=n_new)
+        if world > 1:
+            dist.all_gather(gathered, ids)          # the path's only exchange: token ids over NVLink
+        return ids, lens
+
+    def step_e2e():
+        ids, lens = model.caption_from_host(host_frames, max_new_tokens=n_new)   # H2D + pipeline + D2H
+        return ids, lens
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, out
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    graph_nodes = 0
+    st = next((v for k, v in model._graphs.items() if k[0] == "greedy"), None)
+    # kernels inside one greedy-decode graph replay (counted once, at capture time, by the library)
+    c0 = lib.vc_launch_count()
+    model.greedy_ids(torch.zeros(B, a.prefix_len, a.gpt_dim, device=dev), None, n_new, use_graph=False)
+    torch.cuda.synchronize()
+    graph_nodes = lib.vc_launch_count() - c0
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = lib.vc_launch_count()
+    ms, (ids, lens) = timed(step_resident, args.steps)
+    live = lib.vc_launch_count() - l0
+    clocks = sampler.stop()
+    launches = live + args.steps * graph_nodes
+    per_step_ms = ms / args.steps
+    value = world * B * args.steps / (ms / 1e3)
+
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            step_e2e()
+        ms_e, _ = timed(step_e2e, args.steps)
+        e2e = {"value": world * B * args.steps / (ms_e / 1e3), "unit": "captions/s", "h2d_bytes_per_step": int(host_frames.numel()),
+               "d2h_bytes_per_step": int(B * n_new * 4 + B * 4), "ms_per_step": ms_e / args.steps}
+
+    # ---- per-stage and per-kernel evidence (rank 0 only; outside the timed region above) ----
+    line = None
+    if rank == 0:
+        pk = peaks()
+        # stage split of one step, CUDA events on the launch stream
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        torch.cuda.synchronize()
+        ev[0].record()
+        feat, prefix = model.encode_prefix(dev_frames)
+        ev[1].record()
+        model.greedy_ids(prefix, None, n_new)
+        ev[2].record()
+        torch.cuda.synchronize()
+        enc_ms, dec_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+        # decode-step latency: (T(prefill + n_new-1 steps) - T(prefill)) / (n_new-1), graph replays, p50 over iterations
+        full, pre = [], []
+        model.greedy_ids(prefix, None, 1)
+        for _ in range(12):
+            t0, t1, t2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            t0.record(); model.greedy_ids(prefix, None, n_new); t1.record(); model.greedy_ids(prefix, None, 1); t2.record()
+            torch.cuda.synchronize()
+            full.append(t0.elapsed_time(t1)); pre.append(t1.elapsed_time(t2))
+        step_us = sorted((f - p) / (n_new - 1) * 1e3 for f, p in zip(full, pre))
+        step_p50 = step_us[len(step_us) // 2]
+        P0 = a.prefix_len + 1
+        s_mid = P0 + (n_new - 1) / 2.0
+        step_bytes = GPT_WEIGHT_BYTES + B * s_mid * KV_BYTES_PER_TOKEN + B * KV_BYTES_PER_TOKEN
+        # per-kernel CUDA-event timing of one encoder pass (eager launches on the current stream)
+        lib.vc_prof_begin()
+        model.encode_prefix(dev_frames)
+        import ctypes as C
+        mx = 64
+        names = C.create_string_buffer(mx * 48)
+        tms = (C.c_float * mx)(); calls = (C.c_int * mx)(); work = (C.c_double * mx)()
+        n = lib.vc_prof_end(mx, names, tms, calls, work)
+        kern = {}
+        for i in range(n):
+            nm = names.raw[i * 48:(i + 1) * 48].split(b"\0")[0].decode()
+            kern[nm] = {"ms": round(tms[i], 4), "calls": calls[i], "work": work[i]}
+        g_ms = sum(v["ms"] for k, v in kern.items() if k.startswith("gemm_"))
+        g_fl = sum(v["work"] for k, v in kern.items() if k.startswith("gemm_"))
+        g_calls = sum(v["calls"] for k, v in kern.items() if k.startswith("gemm_"))
+        achieved = g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
+        enc_tflops = B * T * VIT_GFLOP_PER_FRAME / 1e3 / (enc_ms / 1e3)
+        roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all epilogues, one ViT encoder pass)",
+                    "achieved": round(achieved, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": round(achieved / pk["tf_sustained"], 4), "peak_source": pk["source"] + " sustained bf16 (kernel timed inside a long step)",
+                    "frac_of_burst": round(achieved / pk["tf_burst"], 4), "launches": g_calls, "avg_launch_ms": round(g_ms / max(g_calls, 1), 4),
+                    "flop_per_launch_avg": g_fl / max(g_calls, 1), "traffic": None,
+                    "encoder_stage_tflops": round(enc_tflops, 1), "encoder_stage_frac": round(enc_tflops / pk["tf_sustained"], 4)}
+        decode = {"bound": "hbm", "step_p50_us": round(step_p50, 1), "bytes_per_step": int(step_bytes),
+                  "achieved": round(step_bytes / (step_p50 * 1e-6) / 1e9, 1), "peak": pk["hbm"], "unit": "GB/s",
+                  "frac": round(step_bytes / (step_p50 * 1e-6) / 1e9 / pk["hbm"], 4), "n_seq": B, "S_range": [P0, P0 + n_new - 1],
+                  "how": "(graph replay of prefill+19 steps - graph replay of prefill) / 19, p50 of 12 iterations"}
+        line = {
+            "metric": "captions/sec (16-frame clips)", "value": round(value, 2), "unit": "captions/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(per_step_ms, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"ViT-B/16 + GPT-2 small, {B} videos x {T} frames 224x224 per GPU, greedy {n_new} tokens "
+                                   f"(BASELINE.json configs[1]; configs[2] layout at N>1), random-init weights",
+                       "videos_per_gpu": B, "global_batch": world * B, "frames": T, "max_new_tokens": n_new,
+                       "parallelism": f"videos sharded over {world} GPU(s), ids all_gather", "chunk_frames": args.chunk_frames,
+                       "l2": "inputs (154 MB uint8 frames) and per-layer activations (>300 MB) exceed the 126 MB L2 every step"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "decode": decode,
+            "stages_ms": {"preprocess+ViT_Encoder+Cross_Modal_Alignment": round(enc_ms, 3), "GPT2_Decoder_Step(x%d)" % n_new: round(dec_ms, 3)},
+            "kernels_one_encoder_pass": kern,
+            "sample_ids": ids[0, :8].tolist(),
+        }
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.cuda.synchronize()
+        cpu, _ = cpu_sample(3, 1, T, n_new)
+        line["cpu_baseline"] = cpu
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

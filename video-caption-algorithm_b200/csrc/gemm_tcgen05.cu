@@ -261,7 +261,11 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
       g_attr_set[MODE] = true;
     }
   }
-  gemm_tcgen05_kernel<MODE><<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+  static const char* const kNames[] = {"gemm_bias", "gemm_gelu_erf", "gemm_gelu_tanh", "gemm_resid", "gemm_f32", "gemm_patch"};
+  {
+    KernelScope ks(kNames[MODE], 2.0 * p.M * static_cast<double>(p.N) * p.K, stream);
+    gemm_tcgen05_kernel<MODE><<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+  }
   VC_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -257,8 +257,15 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(128) vit_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                                                            int tokens, int heads, int s_pad) {
+constexpr int ATT_THREADS = 256;   // 8 warps: 13 query tiles of ViT-B/16 spread 2,2,2,2,2,1,1,1
+
+__device__ __forceinline__ void cp_async_16_zfill(uint32_t smem_dst, const void* gsrc, bool valid) {
+  const int src_bytes = valid ? 16 : 0;   // src-size 0 -> the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 2) vit_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                                                                      int tokens, int heads, int s_pad) {
   extern __shared__ __align__(128) uint8_t smem_att[];
   uint8_t* sQ = smem_att;
   uint8_t* sK = sQ + s_pad * 128;
@@ -268,14 +275,21 @@ __global__ void __launch_bounds__(128) vit_attention_kernel(const __nv_bfloat16*
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const __nv_bfloat16* base = qkv + static_cast<long long>(frame) * tokens * 3 * D + head * HD;
 
-  // global -> shared: 8 x 16-byte chunks per row per matrix; rows >= tokens are zero
-  for (int i = tid; i < s_pad * 8 * 3; i += blockDim.x) {
-    const int which = i / (s_pad * 8);
-    const int rem = i - which * s_pad * 8;
-    const int row = rem >> 3, chunk = rem & 7;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (row < tokens) v = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(row) * 3 * D + which * D) + chunk);
-    *reinterpret_cast<uint4*>(smem_att + which * s_pad * 128 + swz(row, chunk)) = v;
+  // global -> shared with cp.async (all chunks in flight at once): 8 x 16-byte chunks per row per
+  // matrix; rows >= tokens are zero-filled so padded keys/values stay finite
+  {
+    const uint32_t s0 = smem_u32(smem_att);
+    const int per = s_pad * 8;
+    for (int i = tid; i < per * 3; i += ATT_THREADS) {
+      const int which = i / per;
+      const int rem = i - which * per;
+      const int row = rem >> 3, chunk = rem & 7;
+      const bool ok = row < tokens;
+      const __nv_bfloat16* src = base + static_cast<long long>(ok ? row : 0) * 3 * D + which * D + chunk * 8;
+      cp_async_16_zfill(s0 + which * s_pad * 128 + swz(row, chunk), src, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
 
@@ -286,7 +300,7 @@ __global__ void __launch_bounds__(128) vit_attention_kernel(const __nv_bfloat16*
   const int m_tiles = (tokens + 15) >> 4;
   const int k_blocks = (tokens + 63) >> 6;
 
-  for (int mt = warp; mt < m_tiles; mt += 4) {
+  for (int mt = warp; mt < m_tiles; mt += ATT_THREADS / 32) {
     uint32_t qa[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
@@ -400,7 +414,7 @@ int vit_attention(const void* qkv, void* out, int n_frames, int tokens, int head
   }
   const double flops = 4.0 * n_frames * heads * static_cast<double>(tokens) * tokens * HD;
   VC_LAUNCH("vit_attention", flops, s,
-            (vit_attention_kernel<<<n_frames * heads, 128, smem, s>>>(static_cast<const __nv_bfloat16*>(qkv),
+            (vit_attention_kernel<<<n_frames * heads, ATT_THREADS, smem, s>>>(static_cast<const __nv_bfloat16*>(qkv),
                                                                      static_cast<__nv_bfloat16*>(out), tokens, heads, s_pad)));
   VC_CUDA_OK(cudaGetLastError());
   return 0;
