@@ -42,7 +42,7 @@ KV_BYTES_PER_TOKEN = 36_864
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="videos per GPU")
@@ -119,9 +119,10 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.rows = []
+        self.rows = []          # (arrival time, csv row)
         self.proc = None
         self.index = index
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -133,7 +134,13 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.rows.append(ln.strip())
+            self.rows.append((time.time(), ln.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -141,7 +148,11 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for (t, r) in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t)]
+        # the sampler starts before the warm-up (same workload); if the timed region was shorter than one
+        # sampling period, fall back to the samples taken under the warm-up load just before it
+        use = inside if inside else [r for (_, r) in self.rows[-5:]]
+        for r in use:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -152,7 +163,8 @@ class ClockSampler:
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "window": "timed region" if inside else "warm-up load just before the timed region"}
 
 
 # --------------------------------------------------------------------------- our arm
@@ -214,6 +226,8 @@ def run_b200(args):
             ms = t.item()
         return ms, out
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_resident()
     graph_nodes = 0
@@ -224,10 +238,10 @@ def run_b200(args):
     torch.cuda.synchronize()
     graph_nodes = lib.vc_launch_count() - c0
 
-    sampler = ClockSampler(local)
-    sampler.start()
     l0 = lib.vc_launch_count()
+    sampler.mark_begin()
     ms, (ids, lens) = timed(step_resident, args.steps)
+    sampler.mark_end()
     live = lib.vc_launch_count() - l0
     clocks = sampler.stop()
     launches = live + args.steps * graph_nodes

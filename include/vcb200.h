@@ -150,6 +150,21 @@ int vc_greedy_decode(const VcGptWeights* w, const float* prefix, int n_seq, int 
                      int max_new, int eos, VcKvCache* cache, void* workspace, size_t workspace_bytes, int32_t* ids_out,
                      int32_t* len_out, const int32_t* forced_ids, float* step_logits, vc_stream_t stream);
 
+/* ---- decode-step building block: split-K weight-streaming GEMM for M <= 128 live sequences.
+ *      partial fp32 [ksplit][M][N]; consumers sum the slices in order (ksplit 0 = library's choice) ---- */
+int vc_skinny_ksplit(int N, int K);
+int vc_skinny_gemm_partial(const void* x_bf16, const void* w_bf16, float* partial, int M, int N, int K, int ksplit, vc_stream_t stream);
+
+/* ---- a10  HF generate on device: log-softmax + RepetitionPenalty/NoRepeatNGram/MinNewTokens processors +
+ *      running beam scores + top-K continuations per video (K = 2*num_beams); raw_logits=1 is HF greedy
+ *      (processors on raw logits, K=1).  seqs int32 [n_rows, max_len] = tokens generated so far. ---- */
+int vc_beam_step(const float* logits, long long ld, int vocab, int n_rows, int rows_per_item, const int32_t* seqs, int max_len, int cur_len,
+                 const float* running_scores, float repetition_penalty, int no_repeat_ngram, int min_new_tokens, int eos, int raw_logits,
+                 int K, float* cand_score /*[n_rows,K]*/, int32_t* cand_tok /*[n_rows,K]*/, float* top_score /*[n_rows/rows_per_item,K]*/,
+                 int32_t* top_idx /*flat beam*vocab+token*/, vc_stream_t stream);
+/* KV-cache beam reorder as an index update: slot_out[r][p] = slot_in[src_rows[r]][p] for p < upto */
+int vc_beam_reorder(const int32_t* slot_in, int32_t* slot_out, const int32_t* src_rows, int n_seq, int s_max, int upto, vc_stream_t stream);
+
 /* ---- token selection on given logits (bit-exact vs torch.argmax / topk) ------------------- */
 int vc_argmax_f32(const float* logits, int rows, int vocab, int32_t* out, vc_stream_t stream);
 

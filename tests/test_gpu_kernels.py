@@ -232,3 +232,66 @@ def test_argmax_bit_exact_with_ties(lib):
     torch.cuda.synchronize()
     assert out.cpu().tolist() == torch.argmax(logits, dim=-1).tolist()
     assert out[3].item() == 100 and out[5].item() == 0 and out[7].item() == V - 1
+
+
+# ------------------------------------------------------------------ decode-step skinny GEMM (split-K partials)
+@pytest.mark.parametrize("M,N,K,ks", [(64, 2304, 768, 0), (64, 768, 3072, 0), (3, 768, 768, 12), (128, 3072, 768, 3), (64, 50432, 768, 1),
+                                      (100, 1024, 4096, 0)])
+def test_skinny_gemm_partials_sum_to_product(lib, M, N, K, ks):
+    torch.manual_seed(M + N)
+    x = (torch.randn(M, K, device=DEV) * 0.5).to(torch.bfloat16)
+    W = (torch.randn(N, K, device=DEV) * 0.05).to(torch.bfloat16)
+    ksplit = ks or lib.vc_skinny_ksplit(N, K)
+    P = torch.full((ksplit, M, N), 7.0, device=DEV)
+    L.check(lib.vc_skinny_gemm_partial(x.data_ptr(), W.data_ptr(), P.data_ptr(), M, N, K, ksplit, _stream()))
+    torch.cuda.synchronize()
+    ref = x.float() @ W.float().t()
+    assert (P.sum(0) - ref).abs().max().item() < 2e-3          # fp32 accumulate; order differs from cuBLAS only
+    P2 = torch.empty_like(P)
+    L.check(lib.vc_skinny_gemm_partial(x.data_ptr(), W.data_ptr(), P2.data_ptr(), M, N, K, ksplit, _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(P, P2)                                  # deterministic: no atomics
+
+
+# ------------------------------------------------------------------ HF logits processors + top-K continuations (bit-exact ids)
+@pytest.mark.parametrize("raw", [0, 1])
+def test_beam_step_matches_oracle_processors(lib, raw):
+    torch.manual_seed(9)
+    B, nb, V, max_len, cur_len = 3, 4, 50257, 12, 7
+    K = 1 if raw else 2 * nb
+    rows = B * (1 if raw else nb)
+    per_item = 1 if raw else nb
+    logits = torch.randn(rows, V) * 2
+    seqs = torch.randint(0, V, (rows, max_len))
+    seqs[:, 3] = seqs[:, 1]; seqs[:, 4] = seqs[:, 2]; seqs[:, 5] = seqs[:, 1]; seqs[:, 6] = seqs[:, 2]   # repeated bigram -> banned token
+    running = torch.randn(rows) * 3
+    if raw:
+        sc = O.apply_processors(logits, seqs[:, :cur_len], cur_len, repetition_penalty=1.1, no_repeat_ngram_size=3, min_new_tokens=8, eos=50256)
+        ref_idx = sc.argmax(-1).view(rows, 1)
+        ref_val = sc.max(-1).values.view(rows, 1)
+    else:
+        lp = torch.log_softmax(logits, -1)
+        sc = O.apply_processors(lp, seqs[:, :cur_len], cur_len, repetition_penalty=1.1, no_repeat_ngram_size=3, min_new_tokens=8, eos=50256)
+        cand = (sc.view(B, nb, V) + running.view(B, nb, 1)).view(B, nb * V)
+        ref_val, ref_idx = torch.topk(cand, K, dim=1)
+    d = lambda t, dt: t.to(DEV).to(dt).contiguous()
+    cs = torch.empty(rows, K, device=DEV); ct = torch.empty(rows, K, device=DEV, dtype=torch.int32)
+    ts = torch.empty(rows // per_item, K, device=DEV); ti = torch.empty(rows // per_item, K, device=DEV, dtype=torch.int32)
+    lg, sq, rn = d(logits, torch.float32), d(seqs, torch.int32), d(running, torch.float32)
+    L.check(lib.vc_beam_step(lg.data_ptr(), V, V, rows, per_item, sq.data_ptr(), max_len, cur_len, rn.data_ptr(), 1.1, 3, 8, 50256, raw, K,
+                             cs.data_ptr(), ct.data_ptr(), ts.data_ptr(), ti.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    assert ti.cpu().tolist() == ref_idx.tolist()
+    assert (ts.cpu() - ref_val).abs().max().item() < 2e-5
+
+
+def test_beam_reorder_is_index_select(lib):
+    n_seq, s_max, upto = 12, 9, 6
+    slot_in = torch.randint(0, n_seq, (n_seq, s_max), dtype=torch.int32)
+    src = torch.randint(0, n_seq, (n_seq,), dtype=torch.int32)
+    out = torch.full((n_seq, s_max), -1, dtype=torch.int32).to(DEV)
+    L.check(lib.vc_beam_reorder(slot_in.to(DEV).data_ptr(), out.data_ptr(), src.to(DEV).data_ptr(), n_seq, s_max, upto, _stream()))
+    torch.cuda.synchronize()
+    ref = torch.full((n_seq, s_max), -1, dtype=torch.int32)
+    ref[:, :upto] = slot_in[src.long(), :upto]
+    assert torch.equal(out.cpu(), ref)

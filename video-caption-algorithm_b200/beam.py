@@ -1,0 +1,191 @@
+"""HF-`generate` semantics for `decoder.generate` (src/models/text_decoder.py:131-144) on the
+B200 path: greedy with logits processors (num_beams == 1) and beam search (num_beams > 1).
+
+Heavy work per step runs on the device through the C ABI: the GPT-2 forward over all running
+rows, log-softmax + RepetitionPenalty / NoRepeatNGram / MinNewTokens processors + running
+scores + the top-2*num_beams continuation search (`vc_beam_step`), and the KV-cache beam
+reorder as a slot-table update (`vc_beam_reorder`) instead of HF's per-layer index_select.
+What stays on the host is the bookkeeping over B x 2*num_beams candidates per step
+(transformers `_get_running_beams_for_next_iteration`, `_update_finished_beams`,
+`_check_early_stop_heuristic`) — a few hundred scalars, one small D2H/H2D
+pair per step (HF's own loop synchronises every step as well).
+
+The prefill runs ONCE per video (B rows); the num_beams-fold replication HF performs is
+expressed through the slot table (every beam of a video reads the prompt positions from the
+video's row), and the first selection step merges over one row per video because beams
+1..nb-1 start at -1e9 and cannot reach the top 2*num_beams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List
+
+import torch
+
+from . import lib as L
+from .memory import KvCache
+
+EOS = 50256
+NEG = -1.0e9
+
+
+def beam_search_ids(m, prefix: torch.Tensor, prompt_ids: List[int], *, max_new_tokens: int, num_beams: int,
+                    no_repeat_ngram_size: int = 3, repetition_penalty: float = 1.1, min_new_tokens: int = 8,
+                    length_penalty: float = 1.0, eos: int = EOS):
+    if num_beams == 1:
+        return _greedy_with_processors(m, prefix, prompt_ids, max_new_tokens, no_repeat_ngram_size, repetition_penalty,
+                                       min_new_tokens, eos)
+    d = m.dims
+    dev = m.device
+    lib = L.load()
+    gpt = C.byref(m.packed.gpt)
+    B, P, H = prefix.shape
+    nb, V, ld = num_beams, d["vocab"], d["vocab_pad"]
+    K = 2 * nb
+    n_rows = B * nb
+    Lp = len(prompt_ids)
+    L0 = P + Lp
+    s_max = L0 + max_new_tokens
+    st = L.current_stream
+
+    cache = KvCache(d["gpt_layers"], n_rows, d["gpt_heads"], s_max, 64, dev, with_slots=True)
+    # every beam row of video b reads the prompt positions from physical row b (prefilled once)
+    slot_a = cache.slot
+    slot_a[:, :L0] = (torch.arange(n_rows, device=dev, dtype=torch.int32) // nb).view(n_rows, 1)
+    slot_b = slot_a.clone()
+    ws = torch.empty(lib.vc_gpt_workspace_bytes(gpt, n_rows, max(n_rows, B * L0)), device=dev, dtype=torch.uint8)
+    logits = torch.empty(n_rows, ld, device=dev, dtype=torch.float32)
+    embeds = torch.empty(n_rows, H, device=dev, dtype=torch.float32)
+    cand_score = torch.empty(n_rows, K, device=dev, dtype=torch.float32)
+    cand_tok = torch.empty(n_rows, K, device=dev, dtype=torch.int32)
+    top_score = torch.empty(B, K, device=dev, dtype=torch.float32)
+    top_idx = torch.empty(B, K, device=dev, dtype=torch.int32)
+    seqs_dev = torch.full((n_rows, max_new_tokens), eos, device=dev, dtype=torch.int32)
+    run_dev = torch.zeros(n_rows, device=dev, dtype=torch.float32)
+    tok_dev = torch.empty(n_rows, device=dev, dtype=torch.int32)
+    src_dev = torch.empty(n_rows, device=dev, dtype=torch.int32)
+
+    # ---- prefill: [prefix | wte(prompt)] for the B videos
+    prompt = torch.tensor(prompt_ids, device=dev, dtype=torch.int32)
+    tok_emb = torch.empty(Lp, H, device=dev, dtype=torch.float32)
+    L.check(lib.vc_gpt2_embed_tokens(gpt, prompt.data_ptr(), Lp, tok_emb.data_ptr(), st()))
+    x0 = torch.cat([prefix.to(device=dev, dtype=torch.float32), tok_emb.unsqueeze(0).expand(B, -1, -1)], dim=1).contiguous()
+    L.check(lib.vc_gpt2_forward(gpt, x0.data_ptr(), B, L0, 0, C.byref(cache.c), ws.data_ptr(), ws.numel(), logits.data_ptr(), 0, st()))
+
+    # ---- host-side beam state (transformers `_beam_search` variable names in comments)
+    running_scores = torch.zeros(B, nb)
+    running_scores[:, 1:] = NEG
+    running_seqs = torch.full((B, nb, max_new_tokens), eos, dtype=torch.int64)
+    fin_seqs = running_seqs.clone()                       # sequences
+    fin_scores = torch.full((B, nb), NEG)                 # beam_scores
+    fin_done = torch.zeros(B, nb, dtype=torch.bool)       # is_sent_finished
+    fin_len = torch.zeros(B, nb, dtype=torch.int64)
+    unsatisfied = torch.ones(B, 1, dtype=torch.bool)      # is_early_stop_heuristic_unsatisfied
+    in_top = torch.arange(K).view(1, K) < nb              # top_num_beam_mask
+    cur_len = 0
+    while True:
+        first = cur_len == 0
+        rows, per_item = (B, 1) if first else (n_rows, nb)
+        L.check(lib.vc_beam_step(logits.data_ptr(), ld, V, rows, per_item, seqs_dev.data_ptr(), max_new_tokens, cur_len,
+                                 run_dev.data_ptr(), float(repetition_penalty), int(no_repeat_ngram_size), int(min_new_tokens), eos, 0,
+                                 K, cand_score.data_ptr(), cand_tok.data_ptr(), top_score.data_ptr(), top_idx.data_ptr(), st()))
+        top_scores = top_score.cpu()                      # the per-step sync (B x 2nb floats)
+        flat = top_idx.cpu().to(torch.int64)
+        top_beam, top_tok = flat // V, flat % V
+        cand_seqs = torch.gather(running_seqs, 1, top_beam.unsqueeze(-1).expand(-1, -1, max_new_tokens)).clone()
+        cand_seqs[:, :, cur_len] = top_tok
+        new_len = cur_len + 1
+        hit_stop = (top_tok == eos) | (new_len >= max_new_tokens)
+        run_rank = top_scores + hit_stop.float() * NEG
+        running_scores, pick = torch.topk(run_rank, nb, dim=1)
+        running_seqs = torch.gather(cand_seqs, 1, pick.unsqueeze(-1).expand(-1, -1, max_new_tokens))
+        running_beam = torch.gather(top_beam, 1, pick)
+        running_tok = torch.gather(top_tok, 1, pick)
+        newly = hit_stop & in_top
+        f_scores = top_scores / (float(new_len) ** length_penalty)
+        f_scores = f_scores + (~unsatisfied).float() * NEG
+        f_scores = f_scores + (~newly).float() * NEG
+        merged_scores = torch.cat([fin_scores, f_scores], dim=1)
+        merged_seqs = torch.cat([fin_seqs, cand_seqs], dim=1)
+        merged_done = torch.cat([fin_done, newly], dim=1)
+        merged_len = torch.cat([fin_len, torch.full((B, K), new_len, dtype=torch.int64)], dim=1)
+        fin_scores, sel = torch.topk(merged_scores, nb, dim=1)
+        fin_seqs = torch.gather(merged_seqs, 1, sel.unsqueeze(-1).expand(-1, -1, max_new_tokens))
+        fin_done = torch.gather(merged_done, 1, sel)
+        fin_len = torch.gather(merged_len, 1, sel)
+        cur_len = new_len
+        best_running = running_scores[:, :1] / (float(cur_len) ** length_penalty)
+        worst_fin = torch.where(fin_done, fin_scores.min(dim=1, keepdim=True).values, torch.full_like(fin_scores, NEG))
+        unsatisfied = unsatisfied & (best_running > worst_fin).any(dim=-1, keepdim=True)
+        if not (bool(unsatisfied.any()) and not bool(hit_stop.all())):
+            break
+        # ---- next forward: reorder the cache by index, feed the chosen tokens
+        src_rows = (running_beam + torch.arange(B).view(B, 1) * nb).reshape(-1).to(torch.int32)
+        src_dev.copy_(src_rows, non_blocking=False)
+        tok_dev.copy_(running_tok.reshape(-1).to(torch.int32))
+        seqs_dev.copy_(running_seqs.reshape(n_rows, max_new_tokens).to(torch.int32))
+        run_dev.copy_(running_scores.reshape(-1))
+        past = L0 + cur_len - 1
+        if not first:
+            # positions written by decode steps follow their beam; prompt positions keep the per-video mapping
+            L.check(lib.vc_beam_reorder(slot_a.data_ptr(), slot_b.data_ptr(), src_dev.data_ptr(), n_rows, s_max, past, st()))
+            slot_a, slot_b = slot_b, slot_a
+            cache.c.slot = slot_a.data_ptr()
+        L.check(lib.vc_gpt2_embed_tokens(gpt, tok_dev.data_ptr(), n_rows, embeds.data_ptr(), st()))
+        L.check(lib.vc_gpt2_forward(gpt, embeds.data_ptr(), n_rows, 1, past, C.byref(cache.c), ws.data_ptr(), ws.numel(),
+                                    logits.data_ptr(), 0, st()))
+    ids = torch.full((B, max_new_tokens), eos, dtype=torch.int32)
+    lengths = fin_len[:, 0].to(torch.int32)
+    for b in range(B):
+        n_tok = int(lengths[b])
+        ids[b, :n_tok] = fin_seqs[b, 0, :n_tok].to(torch.int32)
+    return ids.to(dev), lengths.to(dev)
+
+
+def _greedy_with_processors(m, prefix, prompt_ids, max_new_tokens, ngram, rep_penalty, min_new, eos):
+    """HF greedy (`_sample` with do_sample=False): processors on the raw last-position logits, argmax,
+    finished rows emit pad(=eos), stop when every row has produced eos or at max_new_tokens."""
+    d = m.dims
+    dev = m.device
+    lib = L.load()
+    gpt = C.byref(m.packed.gpt)
+    B, P, H = prefix.shape
+    V, ld = d["vocab"], d["vocab_pad"]
+    Lp = len(prompt_ids)
+    L0 = P + Lp
+    st = L.current_stream
+    cache = KvCache(d["gpt_layers"], B, d["gpt_heads"], L0 + max_new_tokens, 64, dev)
+    ws = torch.empty(lib.vc_gpt_workspace_bytes(gpt, B, B * L0), device=dev, dtype=torch.uint8)
+    logits = torch.empty(B, ld, device=dev, dtype=torch.float32)
+    embeds = torch.empty(B, H, device=dev, dtype=torch.float32)
+    cand_score = torch.empty(B, 1, device=dev, dtype=torch.float32)
+    cand_tok = torch.empty(B, 1, device=dev, dtype=torch.int32)
+    top_score = torch.empty(B, 1, device=dev, dtype=torch.float32)
+    top_idx = torch.empty(B, 1, device=dev, dtype=torch.int32)
+    seqs_dev = torch.full((B, max_new_tokens), eos, device=dev, dtype=torch.int32)
+    tok_dev = torch.empty(B, device=dev, dtype=torch.int32)
+    prompt = torch.tensor(prompt_ids, device=dev, dtype=torch.int32)
+    tok_emb = torch.empty(Lp, H, device=dev, dtype=torch.float32)
+    L.check(lib.vc_gpt2_embed_tokens(gpt, prompt.data_ptr(), Lp, tok_emb.data_ptr(), st()))
+    x0 = torch.cat([prefix.to(device=dev, dtype=torch.float32), tok_emb.unsqueeze(0).expand(B, -1, -1)], dim=1).contiguous()
+    L.check(lib.vc_gpt2_forward(gpt, x0.data_ptr(), B, L0, 0, C.byref(cache.c), ws.data_ptr(), ws.numel(), logits.data_ptr(), 0, st()))
+    seqs = torch.full((B, max_new_tokens), eos, dtype=torch.int64)
+    unfinished = torch.ones(B, dtype=torch.bool)
+    lengths = torch.zeros(B, dtype=torch.int64)
+    for cur_len in range(max_new_tokens):
+        L.check(lib.vc_beam_step(logits.data_ptr(), ld, V, B, 1, seqs_dev.data_ptr(), max_new_tokens, cur_len, 0, float(rep_penalty),
+                                 int(ngram), int(min_new), eos, 1, 1, cand_score.data_ptr(), cand_tok.data_ptr(), top_score.data_ptr(),
+                                 top_idx.data_ptr(), st()))
+        nxt = top_idx.cpu().to(torch.int64).view(-1)
+        nxt = torch.where(unfinished, nxt, torch.full_like(nxt, eos))
+        seqs[:, cur_len] = nxt
+        lengths += unfinished.long()
+        unfinished = unfinished & (nxt != eos)
+        if not bool(unfinished.any()) or cur_len + 1 == max_new_tokens:
+            break
+        seqs_dev.copy_(seqs.to(torch.int32))
+        tok_dev.copy_(nxt.to(torch.int32))
+        L.check(lib.vc_gpt2_embed_tokens(gpt, tok_dev.data_ptr(), B, embeds.data_ptr(), st()))
+        L.check(lib.vc_gpt2_forward(gpt, embeds.data_ptr(), B, 1, L0 + cur_len, C.byref(cache.c), ws.data_ptr(), ws.numel(),
+                                    logits.data_ptr(), 0, st()))
+    return seqs.to(torch.int32).to(dev), lengths.to(torch.int32).to(dev)

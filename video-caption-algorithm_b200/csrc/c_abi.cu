@@ -13,6 +13,7 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 namespace vc {
 
@@ -73,8 +74,10 @@ static VitBuffers carve_vit(const VcVitWeights* w, int chunk_frames, void* base)
 }
 
 struct GptBuffers {
-  float* h; void* xn; void* qkv; void* att; void* hid; float* emb; float* logits; int32_t* finished; int32_t* next; size_t total;
+  float* h; void* xn; void* qkv; void* att; void* hid; float* emb; float* logits; int32_t* finished; int32_t* next; float* partial;
+  size_t total;
 };
+constexpr int kSkinnyMaxRows = 128;   // decode steps with more live sequences use the tcgen05 GEMM
 static GptBuffers carve_gpt(const VcGptWeights* w, int n_seq, int max_rows, void* base) {
   const size_t R = static_cast<size_t>(max_rows);
   uint8_t* p = static_cast<uint8_t*>(base);
@@ -89,6 +92,15 @@ static GptBuffers carve_gpt(const VcGptWeights* w, int n_seq, int max_rows, void
   b.logits = reinterpret_cast<float*>(p + off); off += align_up(static_cast<size_t>(n_seq) * w->vocab_pad * 4, 1024);
   b.finished = reinterpret_cast<int32_t*>(p + off); off += align_up(static_cast<size_t>(n_seq) * 4, 1024);
   b.next = reinterpret_cast<int32_t*>(p + off);     off += align_up(static_cast<size_t>(n_seq) * 4, 1024);
+  {
+    // split-K partials of the skinny decode GEMMs: the widest of the four per-layer products
+    const int H = w->dim, rows = n_seq < kSkinnyMaxRows ? n_seq : kSkinnyMaxRows;
+    size_t m = static_cast<size_t>(skinny_ksplit(3 * H, H)) * 3 * H;
+    m = std::max(m, static_cast<size_t>(skinny_ksplit(H, H)) * H);
+    m = std::max(m, static_cast<size_t>(skinny_ksplit(4 * H, H)) * 4 * H);
+    m = std::max(m, static_cast<size_t>(skinny_ksplit(H, 4 * H)) * H);
+    b.partial = reinterpret_cast<float*>(p + off);  off += align_up(m * rows * 4, 1024);
+  }
   b.total = off;
   return b;
 }
@@ -224,16 +236,44 @@ int vc_linear_bias_f32(const float* x, const float* w, const float* b, float* y,
 
 size_t vc_gpt_workspace_bytes(const VcGptWeights* w, int n_seq, int max_new_rows) { return carve_gpt(w, n_seq, max_new_rows, nullptr).total; }
 
+// Decode step (one new position per sequence, few rows): every product streams its weights once
+// through the skinny split-K kernel; partial sums are folded into the next kernel of the chain.
+static int gpt_step_skinny(const VcGptWeights* w, const float* embeds, int n_seq, int past_len, VcKvCache* cache, const GptBuffers& b,
+                           float* logits_out, cudaStream_t s) {
+  const int H = w->dim, M = n_seq;
+  const int ks_attn = skinny_ksplit(3 * H, H), ks_ap = skinny_ksplit(H, H), ks_fc = skinny_ksplit(4 * H, H), ks_mp = skinny_ksplit(H, 4 * H);
+  int e;
+  if ((e = gpt_add_pos(embeds, w->wpe, b.h, n_seq, 1, past_len, H, s))) return e;
+  if ((e = layernorm_f32_bf16(b.h, w->layer[0].ln1_g, w->layer[0].ln1_b, b.xn, M, H, 1e-5f, s))) return e;
+  for (int l = 0; l < w->layers; ++l) {
+    const VcGptLayer& Ly = w->layer[l];
+    if ((e = skinny_gemm(b.xn, Ly.attn_w, b.partial, M, 3 * H, H, ks_attn, s))) return e;
+    if ((e = gpt_attention(nullptr, b.partial, ks_attn, Ly.attn_b, b.att, cache, l, n_seq, 1, past_len, s))) return e;
+    if ((e = skinny_gemm(b.att, Ly.aproj_w, b.partial, M, H, H, ks_ap, s))) return e;
+    if ((e = resid_ln(b.h, b.partial, ks_ap, Ly.aproj_b, Ly.ln2_g, Ly.ln2_b, b.xn, M, H, 1e-5f, s))) return e;
+    if ((e = skinny_gemm(b.xn, Ly.fc_w, b.partial, M, 4 * H, H, ks_fc, s))) return e;
+    if ((e = bias_act(b.partial, ks_fc, Ly.fc_b, b.hid, M, 4 * H, 1, s))) return e;
+    if ((e = skinny_gemm(b.hid, Ly.mproj_w, b.partial, M, H, 4 * H, ks_mp, s))) return e;
+    const bool last = l + 1 == w->layers;
+    const float* ng = last ? w->lnf_g : w->layer[l + 1].ln1_g;
+    const float* nb = last ? w->lnf_b : w->layer[l + 1].ln1_b;
+    if ((e = resid_ln(b.h, b.partial, ks_mp, Ly.mproj_b, ng, nb, b.xn, M, H, 1e-5f, s))) return e;
+  }
+  // tied lm_head: one K slice, so the "partial" is the logits row itself
+  return skinny_gemm(b.xn, w->wte, logits_out, M, w->vocab_pad, H, 1, s);
+}
+
 static int gpt_forward_impl(const VcGptWeights* w, const float* embeds, int n_seq, int L, int past_len, VcKvCache* cache,
                             const GptBuffers& b, float* logits_out, cudaStream_t s) {
   const int H = w->dim, M = n_seq * L;
   int e;
+  if (L == 1 && n_seq <= kSkinnyMaxRows && w->vocab_pad % 64 == 0) return gpt_step_skinny(w, embeds, n_seq, past_len, cache, b, logits_out, s);
   if ((e = gpt_add_pos(embeds, w->wpe, b.h, n_seq, L, past_len, H, s))) return e;
   for (int l = 0; l < w->layers; ++l) {
     const VcGptLayer& Ly = w->layer[l];
     if ((e = layernorm_f32_bf16(b.h, Ly.ln1_g, Ly.ln1_b, b.xn, M, H, 1e-5f, s))) return e;
     if ((e = gemm_bf16(b.xn, Ly.attn_w, Ly.attn_b, M, 3 * H, H, VC_EPI_BIAS, b.qkv, 3 * H, nullptr, 0, 0, s))) return e;
-    if ((e = gpt_attention(b.qkv, b.att, cache, l, n_seq, L, past_len, s))) return e;
+    if ((e = gpt_attention(b.qkv, nullptr, 0, nullptr, b.att, cache, l, n_seq, L, past_len, s))) return e;
     if ((e = gemm_bf16(b.att, Ly.aproj_w, Ly.aproj_b, M, H, H, VC_EPI_BIAS_RESID_F32, b.h, H, nullptr, 0, 0, s))) return e;
     if ((e = layernorm_f32_bf16(b.h, Ly.ln2_g, Ly.ln2_b, b.xn, M, H, 1e-5f, s))) return e;
     if ((e = gemm_bf16(b.xn, Ly.fc_w, Ly.fc_b, M, 4 * H, H, VC_EPI_BIAS_GELU_TANH, b.hid, 4 * H, nullptr, 0, 0, s))) return e;
@@ -288,6 +328,22 @@ int vc_greedy_decode(const VcGptWeights* w, const float* prefix, int n_seq, int 
   }
   return 0;
 }
+
+int vc_beam_step(const float* logits, long long ld, int vocab, int n_rows, int rows_per_item, const int32_t* seqs, int max_len, int cur_len,
+                 const float* running_scores, float repetition_penalty, int no_repeat_ngram, int min_new_tokens, int eos, int raw_logits,
+                 int K, float* cand_score, int32_t* cand_tok, float* top_score, int32_t* top_idx, vc_stream_t stream) {
+  return beam_step(logits, ld, vocab, n_rows, rows_per_item, seqs, max_len, cur_len, running_scores, repetition_penalty, no_repeat_ngram,
+                   min_new_tokens, eos, raw_logits, K, cand_score, cand_tok, top_score, top_idx, S(stream));
+}
+
+int vc_beam_reorder(const int32_t* slot_in, int32_t* slot_out, const int32_t* src_rows, int n_seq, int s_max, int upto, vc_stream_t stream) {
+  return beam_reorder(slot_in, slot_out, src_rows, n_seq, s_max, upto, S(stream));
+}
+
+int vc_skinny_gemm_partial(const void* x_bf16, const void* w_bf16, float* partial, int M, int N, int K, int ksplit, vc_stream_t stream) {
+  return skinny_gemm(x_bf16, w_bf16, partial, M, N, K, ksplit > 0 ? ksplit : skinny_ksplit(N, K), S(stream));
+}
+int vc_skinny_ksplit(int N, int K) { return skinny_ksplit(N, K); }
 
 int vc_argmax_f32(const float* logits, int rows, int vocab, int32_t* out, vc_stream_t stream) {
   return argmax_f32(logits, vocab, rows, vocab, out, S(stream));

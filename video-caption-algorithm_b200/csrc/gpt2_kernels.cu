@@ -47,9 +47,25 @@ int gpt_add_pos(const float* embeds, const float* wpe, float* h, int n_seq, int 
 constexpr int GHD = 64;
 constexpr int ATT_MAX_S = 1024;   // GPT-2 n_positions
 
-__global__ void __launch_bounds__(128) gpt_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+// 8 consecutive qkv values of one row as packed bf16: either from the bf16 GEMM output (prefill) or
+// bias + the fixed-order sum of the skinny GEMM's split-K partials (decode step), rounded to bf16.
+__device__ __forceinline__ uint4 fetch_qkv8(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ P, int ksplit,
+                                            const float* __restrict__ bias, size_t plane, size_t row, int ld, int col) {
+  if (P == nullptr) return *reinterpret_cast<const uint4*>(qkv + row * ld + col);
+  float4 a = __ldg(reinterpret_cast<const float4*>(bias + col)), b = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+  for (int s = 0; s < ksplit; ++s) {
+    const float* p = P + s * plane + row * ld + col;
+    const float4 u = *reinterpret_cast<const float4*>(p), v = *reinterpret_cast<const float4*>(p + 4);
+    a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+    b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
+  }
+  return make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+}
+
+__global__ void __launch_bounds__(128) gpt_attention_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ P, int ksplit,
+                                                            const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                                                             __nv_bfloat16* __restrict__ kv, const int32_t* __restrict__ slot,
-                                                            int layer, int n_seq, int heads, int s_max, int L, int past_len) {
+                                                            int layer, int n_seq, int rows_total, int heads, int s_max, int L, int past_len) {
   __shared__ float s_p[4][ATT_MAX_S];
   const int seq = blockIdx.x / heads, head = blockIdx.x - seq * heads;
   const int H = heads * GHD;
@@ -58,11 +74,12 @@ __global__ void __launch_bounds__(128) gpt_attention_kernel(const __nv_bfloat16*
   __nv_bfloat16* kbase = kv + (static_cast<long long>(layer) * 2 + 0) * plane;
   __nv_bfloat16* vbase = kv + (static_cast<long long>(layer) * 2 + 1) * plane;
   const long long own = (static_cast<long long>(seq) * heads + head) * s_max * GHD;
+  const size_t plane_p = static_cast<size_t>(rows_total) * 3 * H;
 
   // append new K/V rows (16-byte chunks: 8 per row)
   for (int i = tid; i < L * 16; i += blockDim.x) {
     const int l = i >> 4, which = (i >> 3) & 1, chunk = i & 7;
-    const uint4 v = *(reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(seq) * L + l) * 3 * H + (1 + which) * H + head * GHD) + chunk);
+    const uint4 v = fetch_qkv8(qkv, P, ksplit, bias, plane_p, static_cast<size_t>(seq) * L + l, 3 * H, (1 + which) * H + head * GHD + chunk * 8);
     __nv_bfloat16* dst = (which ? vbase : kbase) + own + static_cast<long long>(past_len + l) * GHD;
     reinterpret_cast<uint4*>(dst)[chunk] = v;
   }
@@ -72,11 +89,10 @@ __global__ void __launch_bounds__(128) gpt_attention_kernel(const __nv_bfloat16*
   for (int l = warp; l < L; l += 4) {
     const int n_keys = past_len + l + 1;   // causal
     // q in registers: every lane holds the full 64-dim query (bf16 pairs)
-    const uint4* qp = reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(seq) * L + l) * 3 * H + head * GHD);
     float q[GHD];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const uint4 u = __ldg(qp + c);
+      const uint4 u = fetch_qkv8(qkv, P, ksplit, bias, plane_p, static_cast<size_t>(seq) * L + l, 3 * H, head * GHD + c * 8);
       const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
       q[c * 8 + 0] = a.x; q[c * 8 + 1] = a.y; q[c * 8 + 2] = b.x; q[c * 8 + 3] = b.y;
       q[c * 8 + 4] = cc.x; q[c * 8 + 5] = cc.y; q[c * 8 + 6] = d.x; q[c * 8 + 7] = d.y;
@@ -123,16 +139,125 @@ __global__ void __launch_bounds__(128) gpt_attention_kernel(const __nv_bfloat16*
   }
 }
 
-int gpt_attention(const void* qkv, void* out, const VcKvCache* c, int layer, int n_seq, int L, int past_len, cudaStream_t s) {
+// Short-context variant (past_len + L <= 256, i.e. every caption): all K/V rows of this (seq, head) are staged
+// in shared memory with every thread issuing independent 16-byte loads, so a decode step pays about two
+// memory round trips instead of one per key.  Rows are padded to 144 B (conflict-free 16-byte reads).
+constexpr int ATT_SMEM_MAX_S = 256;
+constexpr int ATT_ROW_B = 144;
+__global__ void __launch_bounds__(128) gpt_attention_smem_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ P, int ksplit,
+                                                                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+                                                                 __nv_bfloat16* __restrict__ kv, const int32_t* __restrict__ slot, int layer,
+                                                                 int n_seq, int rows_total, int heads, int s_max, int L, int past_len) {
+  extern __shared__ __align__(16) uint8_t s_kv[];            // K rows then V rows, ATT_ROW_B bytes each
+  __shared__ float s_p[4][ATT_SMEM_MAX_S];
+  const int seq = blockIdx.x / heads, head = blockIdx.x - seq * heads;
+  const int H = heads * GHD;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_total = past_len + L;
+  const long long plane = static_cast<long long>(n_seq) * heads * s_max * GHD;
+  __nv_bfloat16* kbase = kv + (static_cast<long long>(layer) * 2 + 0) * plane;
+  __nv_bfloat16* vbase = kv + (static_cast<long long>(layer) * 2 + 1) * plane;
+  const long long own = (static_cast<long long>(seq) * heads + head) * s_max * GHD;
+  const size_t plane_p = static_cast<size_t>(rows_total) * 3 * H;
+  uint8_t* sK = s_kv;
+  uint8_t* sV = s_kv + n_total * ATT_ROW_B;
+  float* sQ = reinterpret_cast<float*>(s_kv + 2 * n_total * ATT_ROW_B);   // [L][64] fp32 (bf16-rounded values)
+  for (int i = tid; i < n_total * 16 + L * 8; i += blockDim.x) {
+    if (i >= n_total * 16) {                                             // query rows
+      const int qi = i - n_total * 16, l = qi >> 3, chunk = qi & 7;
+      const uint4 u = fetch_qkv8(qkv, P, ksplit, bias, plane_p, static_cast<size_t>(seq) * L + l, 3 * H, head * GHD + chunk * 8);
+      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      float4* dst = reinterpret_cast<float4*>(sQ + l * GHD + chunk * 8);
+      dst[0] = make_float4(a.x, a.y, b.x, b.y);
+      dst[1] = make_float4(cc.x, cc.y, d.x, d.y);
+      continue;
+    }
+    const int j = i >> 4, which = (i >> 3) & 1, chunk = i & 7;
+    uint4 v;
+    if (j < past_len) {
+      const int phys = slot != nullptr ? slot[static_cast<long long>(seq) * s_max + j] : seq;
+      const __nv_bfloat16* src = (which ? vbase : kbase) + (static_cast<long long>(phys) * heads + head) * s_max * GHD + static_cast<long long>(j) * GHD;
+      v = reinterpret_cast<const uint4*>(src)[chunk];
+    } else {
+      v = fetch_qkv8(qkv, P, ksplit, bias, plane_p, static_cast<size_t>(seq) * L + (j - past_len), 3 * H, (1 + which) * H + head * GHD + chunk * 8);
+      reinterpret_cast<uint4*>((which ? vbase : kbase) + own + static_cast<long long>(j) * GHD)[chunk] = v;   // append to the cache
+    }
+    *reinterpret_cast<uint4*>((which ? sV : sK) + j * ATT_ROW_B + chunk * 16) = v;
+  }
+  __syncthreads();
+  const float scale = 0.125f;
+  for (int l = warp; l < L; l += 4) {
+    const int n_keys = past_len + l + 1;
+    float q[GHD];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float4 f = reinterpret_cast<const float4*>(sQ + l * GHD)[c];   // broadcast read
+      q[c * 4 + 0] = f.x; q[c * 4 + 1] = f.y; q[c * 4 + 2] = f.z; q[c * 4 + 3] = f.w;
+    }
+    float mx = -INFINITY;
+    for (int j = lane; j < n_keys; j += 32) {
+      const uint4* kp = reinterpret_cast<const uint4*>(sK + j * ATT_ROW_B);
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 u = kp[c];
+        const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+        acc = fmaf(q[c * 8 + 0], a.x, acc); acc = fmaf(q[c * 8 + 1], a.y, acc);
+        acc = fmaf(q[c * 8 + 2], b.x, acc); acc = fmaf(q[c * 8 + 3], b.y, acc);
+        acc = fmaf(q[c * 8 + 4], cc.x, acc); acc = fmaf(q[c * 8 + 5], cc.y, acc);
+        acc = fmaf(q[c * 8 + 6], d.x, acc); acc = fmaf(q[c * 8 + 7], d.y, acc);
+      }
+      acc *= scale;
+      s_p[warp][j] = acc;
+      mx = fmaxf(mx, acc);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < n_keys; j += 32) {
+      const float p = __expf(s_p[warp][j] - mx);
+      s_p[warp][j] = p;
+      sum += p;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < n_keys; ++j) {
+      const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(sV + j * ATT_ROW_B + lane * 4));
+      const float p = s_p[warp][j];
+      o0 = fmaf(p, v.x, o0);
+      o1 = fmaf(p, v.y, o1);
+    }
+    const float inv = 1.f / sum;
+    *(reinterpret_cast<uint32_t*>(out + (static_cast<long long>(seq) * L + l) * H + head * GHD) + lane) = pack_bf16(o0 * inv, o1 * inv);
+    __syncwarp();
+  }
+}
+
+int gpt_attention(const void* qkv, const float* P, int ksplit, const float* bias, void* out, const VcKvCache* c, int layer, int n_seq,
+                  int L, int past_len, cudaStream_t s) {
   VC_REQUIRE(c->head_dim == GHD, "gpt_attention: head_dim=%d (only 64 is built)", c->head_dim);
   VC_REQUIRE(past_len + L <= c->s_max && c->s_max <= ATT_MAX_S, "gpt_attention: %d+%d positions exceed cache s_max=%d", past_len, L, c->s_max);
   VC_REQUIRE(n_seq <= c->n_seq && layer < c->layers, "gpt_attention: cache too small");
   if (n_seq <= 0 || L <= 0) return 0;
   const double bytes = static_cast<double>(n_seq) * c->heads * GHD * 2.0 * (2.0 * L + 2.0 * (past_len + L));
+  if (past_len + L <= ATT_SMEM_MAX_S) {
+    const int smem = 2 * (past_len + L) * ATT_ROW_B + L * GHD * 4;
+    static int attr = 0;
+    if (smem > attr && smem > 32 * 1024) {
+      VC_CUDA_OK(cudaFuncSetAttribute(gpt_attention_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_MAX_S * (2 * ATT_ROW_B + GHD * 4)));
+      attr = ATT_SMEM_MAX_S * (2 * ATT_ROW_B + GHD * 4);
+    }
+    VC_LAUNCH("gpt_attention", bytes, s,
+              (gpt_attention_smem_kernel<<<n_seq * c->heads, 128, smem, s>>>(static_cast<const __nv_bfloat16*>(qkv), P, ksplit, bias,
+                                                                         static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(c->kv),
+                                                                         c->slot, layer, c->n_seq, n_seq * L, c->heads, c->s_max, L, past_len)));
+    VC_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   VC_LAUNCH("gpt_attention", bytes, s,
-            (gpt_attention_kernel<<<n_seq * c->heads, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out),
-                                                                  static_cast<__nv_bfloat16*>(c->kv), c->slot, layer, c->n_seq, c->heads,
-                                                                  c->s_max, L, past_len)));
+            (gpt_attention_kernel<<<n_seq * c->heads, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), P, ksplit, bias,
+                                                                  static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(c->kv), c->slot,
+                                                                  layer, c->n_seq, n_seq * L, c->heads, c->s_max, L, past_len)));
   VC_CUDA_OK(cudaGetLastError());
   return 0;
 }

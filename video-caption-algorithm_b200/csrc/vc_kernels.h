@@ -44,8 +44,16 @@ int linear_bias_f32(const float* x, const float* w, const float* b, float* y, in
 
 // gpt2_kernels.cu
 int gpt_add_pos(const float* embeds, const float* wpe, float* h, int n_seq, int L, int past_len, int dim, cudaStream_t s);
-int gpt_attention(const void* qkv, void* out, const VcKvCache* cache, int layer, int n_seq, int L, int past_len,
-                  cudaStream_t s);
+// qkv: bf16 [rows, 3H] (prefill) or, when P != null, fp32 split-K partials [ksplit][rows][3H] + bias (decode step)
+int gpt_attention(const void* qkv, const float* P, int ksplit, const float* bias, void* out, const VcKvCache* cache, int layer,
+                  int n_seq, int L, int past_len, cudaStream_t s);
+
+// skinny_gemm.cu (decode step, M <= 128)
+int skinny_ksplit(int N, int K);
+int skinny_gemm(const void* x, const void* W, float* P, int M, int N, int K, int ksplit, cudaStream_t s);
+int resid_ln(float* h, const float* P, int ksplit, const float* bias, const float* gamma, const float* beta, void* xn, int rows, int dim,
+             float eps, cudaStream_t s);
+int bias_act(const float* P, int ksplit, const float* bias, void* out, int M, int N, int gelu, cudaStream_t s);
 int argmax_f32(const float* logits, long long ld, int rows, int vocab, int32_t* out, cudaStream_t s);
 int embed_tokens(const void* wte_bf16, const int32_t* ids, int n, int dim, float* out, cudaStream_t s);
 int greedy_init(int32_t* ids_out, int32_t* len_out, int32_t* finished, int n_seq, int max_new, int eos, cudaStream_t s);
@@ -55,5 +63,11 @@ int greedy_select(const float* logits, long long ld, int vocab, int n_seq, int s
                   int32_t* next_ids, cudaStream_t s);
 int build_prefill_embeds(const float* prefix, const void* wte_bf16, const int32_t* prompt_ids, int n_seq, int P, int Lp,
                          int dim, float* out, cudaStream_t s);
+
+// beam_kernels.cu
+int beam_step(const float* logits, long long ld, int vocab, int n_rows, int rows_per_item, const int32_t* seqs, int max_len, int cur_len,
+              const float* running, float rep_penalty, int ngram, int min_new, int eos, int raw, int K, float* cand_score,
+              int32_t* cand_tok, float* top_score, int32_t* top_idx, cudaStream_t s);
+int beam_reorder(const int32_t* slot_in, int32_t* slot_out, const int32_t* src_rows, int n_seq, int s_max, int upto, cudaStream_t s);
 
 }  // namespace vc

@@ -16,7 +16,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 SO_PATH = CSRC / "libvcb200.so"
-SOURCES = ["gemm_tcgen05.cu", "vit_kernels.cu", "gpt2_kernels.cu", "beam_kernels.cu", "c_abi.cu"]
+SOURCES = ["gemm_tcgen05.cu", "vit_kernels.cu", "gpt2_kernels.cu", "skinny_gemm.cu", "beam_kernels.cu", "c_abi.cu"]
 HEADERS = ["vc_common.cuh", "vc_kernels.h", "../../include/vcb200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -110,6 +110,10 @@ _SIGNATURES = {
     "vc_greedy_decode": (_i, [C.POINTER(VcGptWeights), _p, _i, _i, _p, _i, _i, _i, C.POINTER(VcKvCache), _p, _sz, _p, _p,
                               _p, _p, _p]),
     "vc_argmax_f32": (_i, [_p, _i, _i, _p, _p]),
+    "vc_skinny_ksplit": (_i, [_i, _i]),
+    "vc_skinny_gemm_partial": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
+    "vc_beam_step": (_i, [_p, C.c_longlong, _i, _i, _i, _p, _i, _i, _p, _f, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "vc_beam_reorder": (_i, [_p, _p, _p, _i, _i, _i, _p]),
 }
 EXPORTS = tuple(_SIGNATURES)
 
