@@ -194,12 +194,13 @@ def run_b200(args):
     # this rank's shard: global video indices rank*B .. rank*B+B-1 (reproducible for any world size)
     host_frames = synthetic.make_batch_u8(rank * B, B, T).pin_memory()
     dev_frames = host_frames.to(dev)
-    gathered = [torch.empty(B, n_new, device=dev, dtype=torch.int32) for _ in range(world)] if world > 1 else None
+    from vcb200.sharding import gather_ids, shard_range
+    assert shard_range(world * B, world, rank) == (rank * B, rank * B + B)
 
     def step_resident():
         ids, lens = model.caption_ids(dev_frames, max_new_tokens=n_new)
         if world > 1:
-            dist.all_gather(gathered, ids)          # the path's only exchange: token ids over NVLink
+            gather_ids(ids, lens, world * B)        # the path's only exchange: token ids (+lengths) over NVLink
         return ids, lens
 
     def step_e2e():

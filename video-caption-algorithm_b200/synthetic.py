@@ -57,6 +57,8 @@ ARCHS = {
     "vit_l14_gpt2m": Arch("vit_l14_gpt2m", 224, 14, 1024, 24, 16, 4096, 256, 1024, 24, 16, 50257, 1024, 4),
     # 2-layer cut of the B/16 pair: same widths, fast enough for CPU-side tests
     "tiny": Arch("tiny", 224, 16, 768, 2, 12, 3072, 256, 768, 2, 12, 50257, 1024, 4),
+    # 2-layer cut of the L/14 + medium pair (patch K=588 padded to 640, 257 tokens, 16 heads, width 1024)
+    "tiny_l14": Arch("tiny_l14", 224, 14, 1024, 2, 16, 4096, 256, 1024, 2, 16, 50257, 1024, 4),
 }
 
 
