@@ -1,12 +1,18 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a:  C[M,N] = epi(A[M,K] * W[N,K]^T)
 //
-//   * operands staged by TMA (cp.async.bulk.tensor, SWIZZLE_128B) through a 4-deep
-//     mbarrier ring, 128x256x64 tiles;
-//   * one elected thread issues tcgen05.mma (cta_group::1, M=128, N=256, K=16),
-//     fp32 accumulators live in TMEM, double-buffered (2 x 256 columns) so the
-//     epilogue of tile i overlaps the MMAs of tile i+1;
-//   * 8 epilogue warps read TMEM with tcgen05.ld (one accumulator row per thread)
-//     and fuse bias / GELU / residual-add / patch-embed scatter before storing.
+//   * CTA pairs (cluster of 2, tcgen05 cta_group::2): one 256x256 output tile per pair, each CTA
+//     stages its 128 rows of A and its 128 rows of W per 64-wide K block, so a pair moves 64 KB
+//     per 8.4 MFLOP (128 flop/B) instead of the 85 flop/B of a single-CTA 128x256 tile — the
+//     L2->SM fill rate, not the tensor pipe, was the limit of the single-CTA version;
+//   * operands staged by TMA (cp.async.bulk.tensor, SWIZZLE_128B) through a 6-deep mbarrier
+//     ring; both CTAs' loads complete on the leader's "full" barrier, the MMA's tcgen05.commit
+//     multicasts the "empty" arrive to both CTAs;
+//   * one elected thread of the leader CTA issues tcgen05.mma (M=256, N=256, K=16); fp32
+//     accumulators live in TMEM (128 lanes x 256 columns per CTA), double-buffered so the epilogue
+//     of tile i overlaps the MMAs of tile i+1;
+//   * 8 epilogue warps per CTA read TMEM with tcgen05.ld (one accumulator row per thread),
+//     transpose 32x32 blocks through swizzled shared memory and then apply bias / GELU /
+//     residual-add / patch-embed scatter with fully coalesced global accesses.
 //
 // This is the dense contraction of the ViT frame encoder (reference:
 // src/models/video_encoder.py:288-326 -> torchvision/timm Linear + Conv2d patch
@@ -23,15 +29,18 @@ namespace vc {
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, UK = 16;
-constexpr int STAGES = 4;
-constexpr int A_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_BYTES = BN * BK * 2;   // 32 KB
+constexpr int BM = 128;                // rows of A per CTA; a pair covers 256
+constexpr int BN = 256;                // columns per pair tile; each CTA stages BN/2 rows of W
+constexpr int BK = 64, UK = 16;
+constexpr int STAGES = 6;
+constexpr int A_BYTES = BM * BK * 2;          // 16 KB
+constexpr int B_BYTES = (BN / 2) * BK * 2;    // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int TMEM_COLS = 512;         // 2 accumulators x 256 fp32 columns
 constexpr int EPI_WARPS = 8;
+constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // one 32x32 fp32 block per warp
 constexpr int THREADS = (2 + EPI_WARPS) * 32;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct GemmParams {
   int M, N, K;
@@ -46,118 +55,119 @@ struct GemmParams {
   uint32_t idesc;         // tcgen05 instruction descriptor
 };
 
+// One 32-row x 32-column accumulator block of one warp.  Phase 1: thread = row, raw fp32 accumulators into
+// the warp's staging block (16-byte chunks XOR-swizzled by row: conflict-free both ways).  Phase 2: thread =
+// (row group, 4-column group): 8 lanes cover one 128-byte row segment, so every global access is a full line.
 template <int MODE>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int col0, bool row_ok, const uint32_t (&acc)[32]) {
-  float v[32];
+__device__ __forceinline__ void epilogue_block(const GemmParams& p, uint8_t* stg, int lane, int row_base, int col0, const uint32_t (&acc)[32]) {
+  const uint32_t sbase = smem_u32(stg);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-  if (p.bias != nullptr) {
-    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t a = sbase + lane * 128 + ((j ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(acc[4 * j]), "r"(acc[4 * j + 1]), "r"(acc[4 * j + 2]), "r"(acc[4 * j + 3])
+                 : "memory");
+  }
+  __syncwarp();
+  const int cc = lane & 7, rsub = lane >> 3;
+  const int col = col0 + cc * 4;
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 b = __ldg(b4 + j);
-      v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + rsub;
+    float4 v;
+    const uint32_t a = sbase + rr * 128 + ((cc ^ (rr & 7)) << 4);
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    if (MODE == VC_EPI_BIAS_GELU_ERF) {
+      v.x = gelu_erf_fast(v.x); v.y = gelu_erf_fast(v.y); v.z = gelu_erf_fast(v.z); v.w = gelu_erf_fast(v.w);
+    } else if (MODE == VC_EPI_BIAS_GELU_TANH) {
+      v.x = gelu_tanh_fast(v.x); v.y = gelu_tanh_fast(v.y); v.z = gelu_tanh_fast(v.z); v.w = gelu_tanh_fast(v.w);
+    }
+    const int row = row_base + rr;
+    if (row >= p.M) continue;
+    if (MODE == VC_EPI_BIAS || MODE == VC_EPI_BIAS_GELU_ERF || MODE == VC_EPI_BIAS_GELU_TANH) {
+      uint2 w;
+      w.x = pack_bf16(v.x, v.y);
+      w.y = pack_bf16(v.z, v.w);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col) = w;
+    } else if (MODE == VC_EPI_BIAS_RESID_F32) {
+      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col);
+      const float4 r = *o;
+      *o = make_float4(r.x + v.x, r.y + v.y, r.z + v.z, r.w + v.w);
+    } else if (MODE == VC_EPI_BIAS_F32) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col) = v;
+    } else if (MODE == VC_EPI_PATCH_EMBED) {
+      const int g = row / p.rows_per_group, r = row - g * p.rows_per_group;
+      const size_t orow = static_cast<size_t>(g) * (p.rows_per_group + 1) + 1 + r;
+      const float4 e = __ldg(reinterpret_cast<const float4*>(p.aux + static_cast<size_t>(1 + r) * p.N + col));
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + col) = make_float4(v.x + e.x, v.y + e.y, v.z + e.z, v.w + e.w);
     }
   }
-  if (MODE == VC_EPI_BIAS_GELU_ERF) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-  } else if (MODE == VC_EPI_BIAS_GELU_TANH) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
-  }
-  if (!row_ok) return;
-  if (MODE == VC_EPI_BIAS || MODE == VC_EPI_BIAS_GELU_ERF || MODE == VC_EPI_BIAS_GELU_TANH) {
-    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col0);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 w;
-      w.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-      w.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-      w.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-      w.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-      o[j] = w;
-    }
-  } else if (MODE == VC_EPI_BIAS_RESID_F32) {
-    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 r = o[j];
-      r.x += v[4 * j + 0]; r.y += v[4 * j + 1]; r.z += v[4 * j + 2]; r.w += v[4 * j + 3];
-      o[j] = r;
-    }
-  } else if (MODE == VC_EPI_BIAS_F32) {
-    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-  } else if (MODE == VC_EPI_PATCH_EMBED) {
-    const int g = row / p.rows_per_group, r = row - g * p.rows_per_group;
-    const size_t orow = static_cast<size_t>(g) * (p.rows_per_group + 1) + 1 + r;
-    const float4* pe = reinterpret_cast<const float4*>(p.aux + static_cast<size_t>(1 + r) * p.N + col0);
-    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + col0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 e = __ldg(pe + j);
-      o[j] = make_float4(v[4 * j + 0] + e.x, v[4 * j + 1] + e.y, v[4 * j + 2] + e.z, v[4 * j + 3] + e.w);
-    }
-  }
+  __syncwarp();   // the next block reuses the staging buffer
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B tiles must sit on 1024-byte boundaries
+  // SWIZZLE_128B tiles must sit on 1024-byte boundaries (same offsets in both CTAs of the pair)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator ready
-  uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained
+  uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EPI_WARPS * EPI_STAGE_BYTES);   // used in the leader only
+  uint64_t* empty_bar = full_bar + STAGES;    // per CTA: its smem slot is free (multicast commit)
+  uint64_t* tfull_bar = empty_bar + STAGES;   // [2] per CTA: accumulator ready (multicast commit)
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2] leader only: accumulator drained by both CTAs' epilogues
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = (p.M + BM - 1) / BM;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int m_tiles = (p.M + 2 * BM - 1) / (2 * BM);
   const int n_tiles = (p.N + BN - 1) / BN;
   const int k_blocks = p.K / BK;
   const int total = m_tiles * n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 2 * EPI_WARPS); }
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b); }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) { tmem_alloc_pair(tmem_slot, TMEM_COLS); tmem_relinquish_pair(); }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();          // barriers initialised and TMEM allocated in both CTAs before any cross-CTA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------ TMA producer (one lane)
+    // ------------------------------------------------ TMA producer (one lane per CTA)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+      for (int t = pair; t < total; t += n_pairs) {
+        const int m0 = (t / n_tiles) * (2 * BM) + static_cast<int>(rank) * BM;
+        const int n0 = (t % n_tiles) * BN + static_cast<int>(rank) * (BN / 2);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_2d(&tm_a, &full_bar[stage], sa, kb * BK, m0);
-          tma_load_2d(&tm_b, &full_bar[stage], sa + A_BYTES, kb * BK, n0);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);   // both CTAs' bytes land on this barrier
+          const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          tma_load_2d_pair(&tm_a, full_leader, sa, kb * BK, m0);
+          tma_load_2d_pair(&tm_b, full_leader, sa + A_BYTES, kb * BK, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer (one lane)
-    if (lane == 0) {
+    // ------------------------------------------------ MMA issuer (one lane of the leader CTA)
+    if (leader && lane == 0) {
       const uint32_t idesc = p.idesc;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      for (int t = pair; t < total; t += n_pairs) {
+        mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
@@ -169,27 +179,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             // +32 B per K=16 slice inside the 128 B swizzle row (start address is in 16 B units)
-            tc_mma_bf16(d_tmem, da + p.k_adv * k, db + p.k_adv * k, idesc, (kb | k) != 0);
+            tc_mma_bf16_pair(d_tmem, da + p.k_adv * k, db + p.k_adv * k, idesc, (kb | k) != 0);
           }
-          tc_commit(&empty_bar[stage]);            // smem slot reusable once these MMAs retire
+          tc_commit_pair(&empty_bar[stage], 0x3);   // both CTAs' slots reusable once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tfull_bar[acc]);                // accumulator complete
+        tc_commit_pair(&tfull_bar[acc], 0x3);       // accumulator complete in both CTAs
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // ------------------------------------------------ epilogue warps
+    // ------------------------------------------------ epilogue warps (both CTAs)
     const int ew = warp - 2;            // 0..7
     const int quarter = warp & 3;       // TMEM lane quarter this warp may read
     const int half = ew >> 2;           // which 128 columns of the 256-wide tile
+    uint8_t* stg = epi_stage + ew * EPI_STAGE_BYTES;
+    const uint32_t tempty_leader0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
+    const uint32_t tempty_leader1 = mapa_shared(smem_u32(&tempty_bar[1]), 0);
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x) {
-      const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+    for (int t = pair; t < total; t += n_pairs) {
+      const int m0 = (t / n_tiles) * (2 * BM) + static_cast<int>(rank) * BM;
+      const int n0 = (t % n_tiles) * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int row_base = m0 + quarter * 32;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         const int col_in_tile = half * 128 + c * 32;
@@ -197,20 +210,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_in_tile, r);
         tmem_ld_wait();
         const int col0 = n0 + col_in_tile;
-        if (col0 < p.N) epilogue_chunk<MODE>(p, row, col0, row_ok, r);
+        if (col0 < p.N && row_base < p.M) epilogue_block<MODE>(p, stg, lane, row_base, col0, r);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();          // the peer's smem / TMEM stay alive until every MMA and epilogue is done
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc_pair(tmem_base, TMEM_COLS);
   }
 }
 
@@ -292,14 +305,16 @@ int gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int
   }
   CUtensorMap ta, tb;
   if (int e = make_map(&ta, A, M, K, BM)) return e;
-  if (int e = make_map(&tb, W, N, K, BN)) return e;
+  if (int e = make_map(&tb, W, N, K, BN / 2)) return e;
   GemmParams p{M, N, K, mode, bias, out, ldo, aux, rows_per_group,
                g_dbg_desc_hi ? g_dbg_desc_hi : umma_desc_sw128_hi(),
                g_dbg_k_adv ? g_dbg_k_adv : 2u,
-               g_dbg_idesc ? g_dbg_idesc : umma_idesc_bf16(BM, BN)};
-  const int total = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  int grid = total < g_num_sms ? total : g_num_sms;
-  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+               g_dbg_idesc ? g_dbg_idesc : umma_idesc_bf16(2 * BM, BN)};
+  const int total = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);   // pair tiles
+  int pairs = g_num_sms / 2;
+  if (total < pairs) pairs = total;
+  if (max_ctas > 0 && 2 * pairs > max_ctas) pairs = max_ctas / 2 > 0 ? max_ctas / 2 : 1;
+  const int grid = 2 * pairs;
   switch (mode) {
     case VC_EPI_BIAS: return launch<VC_EPI_BIAS>(ta, tb, p, grid, stream);
     case VC_EPI_BIAS_GELU_ERF: return launch<VC_EPI_BIAS_GELU_ERF>(ta, tb, p, grid, stream);
