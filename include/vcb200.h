@@ -109,8 +109,6 @@ int vc_patchify_f32(const float* video_chw, void* out_bf16, int n_frames, int H,
 /* ---- a2  ViT encoder building blocks + whole encoder: src/models/video_encoder.py:288-326 */
 int vc_gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int K, int epilogue, void* out, int ldo,
                  const float* aux, int rows_per_group, vc_stream_t stream);
-/* bring-up aid: override the UMMA smem-descriptor template / K step / instruction descriptor (0 = built-in) */
-void vc_debug_gemm_override(unsigned long long desc_hi, unsigned int k_adv, unsigned int idesc);
 int vc_layernorm_f32_bf16(const float* x, const float* gamma, const float* beta, void* out_bf16, int rows, int dim,
                           float eps, vc_stream_t stream);
 int vc_vit_attention(const void* qkv_bf16, void* out_bf16, int n_frames, int tokens, int heads, int head_dim,

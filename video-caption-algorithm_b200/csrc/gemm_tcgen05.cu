@@ -50,10 +50,27 @@ struct GemmParams {
   int ldo;                // leading dimension of out (elements)
   const float* aux;       // patch-embed: pos embedding [tokens, N]
   int rows_per_group;     // patch-embed: patches per frame (196); out row = g*(rpg+1)+1+r
-  uint64_t desc_hi;       // smem descriptor without the start address (see umma_desc_sw128)
-  uint32_t k_adv;         // start-address step per K=16 slice, in 16-byte units
-  uint32_t idesc;         // tcgen05 instruction descriptor
 };
+
+// Predicated global accesses as single instructions: a C++ `if` around the store lets the compiler sink the whole
+// epilogue math into a divergent region per row, which serialises the eight unrolled iterations.
+__device__ __forceinline__ void st_pred_v2(void* ptr, uint32_t a, uint32_t b, bool ok) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %0, 0;\n\t@p st.global.v2.b32 [%1], {%2, %3};\n\t}" ::"r"(static_cast<uint32_t>(ok)), "l"(ptr), "r"(a), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void st_pred_v4(void* ptr, float4 v, bool ok) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %0, 0;\n\t@p st.global.v4.f32 [%1], {%2, %3, %4, %5};\n\t}" ::"r"(static_cast<uint32_t>(ok)), "l"(ptr),
+               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float4 ld_pred_v4(const void* ptr, bool ok) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t@p ld.global.v4.f32 {%0, %1, %2, %3}, [%5];\n\t}"
+               : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+               : "r"(static_cast<uint32_t>(ok)), "l"(ptr)
+               : "memory");
+  return v;
+}
 
 // One 32-row x 32-column accumulator block of one warp.  Phase 1: thread = row, raw fp32 accumulators into
 // the warp's staging block (16-byte chunks XOR-swizzled by row: conflict-free both ways).  Phase 2: thread =
@@ -85,23 +102,21 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, uint8_t* stg
       v.x = gelu_tanh_fast(v.x); v.y = gelu_tanh_fast(v.y); v.z = gelu_tanh_fast(v.z); v.w = gelu_tanh_fast(v.w);
     }
     const int row = row_base + rr;
-    if (row >= p.M) continue;
+    const bool ok = row < p.M;
+    const int rowc = ok ? row : 0;
     if (MODE == VC_EPI_BIAS || MODE == VC_EPI_BIAS_GELU_ERF || MODE == VC_EPI_BIAS_GELU_TANH) {
-      uint2 w;
-      w.x = pack_bf16(v.x, v.y);
-      w.y = pack_bf16(v.z, v.w);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col) = w;
+      st_pred_v2(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(rowc) * p.ldo + col, pack_bf16(v.x, v.y), pack_bf16(v.z, v.w), ok);
     } else if (MODE == VC_EPI_BIAS_RESID_F32) {
-      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col);
-      const float4 r = *o;
-      *o = make_float4(r.x + v.x, r.y + v.y, r.z + v.z, r.w + v.w);
+      float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(rowc) * p.ldo + col;
+      const float4 r = ld_pred_v4(o, ok);
+      st_pred_v4(o, make_float4(r.x + v.x, r.y + v.y, r.z + v.z, r.w + v.w), ok);
     } else if (MODE == VC_EPI_BIAS_F32) {
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col) = v;
+      st_pred_v4(reinterpret_cast<float*>(p.out) + static_cast<size_t>(rowc) * p.ldo + col, v, ok);
     } else if (MODE == VC_EPI_PATCH_EMBED) {
-      const int g = row / p.rows_per_group, r = row - g * p.rows_per_group;
+      const int g = rowc / p.rows_per_group, r = rowc - g * p.rows_per_group;
       const size_t orow = static_cast<size_t>(g) * (p.rows_per_group + 1) + 1 + r;
       const float4 e = __ldg(reinterpret_cast<const float4*>(p.aux + static_cast<size_t>(1 + r) * p.N + col));
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + col) = make_float4(v.x + e.x, v.y + e.y, v.z + e.z, v.w + e.w);
+      st_pred_v4(reinterpret_cast<float*>(p.out) + orow * p.ldo + col, make_float4(v.x + e.x, v.y + e.y, v.z + e.z, v.w + e.w), ok);
     }
   }
   __syncwarp();   // the next block reuses the staging buffer
@@ -143,27 +158,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------ TMA producer (one lane per CTA)
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int t = pair; t < total; t += n_pairs) {
-        const int m0 = (t / n_tiles) * (2 * BM) + static_cast<int>(rank) * BM;
-        const int n0 = (t % n_tiles) * BN + static_cast<int>(rank) * (BN / 2);
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ------------------------------------------------ TMA producer (whole warp loops, one elected lane issues)
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t full_leader0 = mapa_shared(smem_u32(&full_bar[0]), 0);
+    for (int t = pair; t < total; t += n_pairs) {
+      const int m0 = (t / n_tiles) * (2 * BM) + static_cast<int>(rank) * BM;
+      const int n0 = (t % n_tiles) * BN + static_cast<int>(rank) * (BN / 2);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * STAGE_BYTES;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);   // both CTAs' bytes land on this barrier
-          const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          const uint32_t full_leader = full_leader0 + stage * 8;
           tma_load_2d_pair(&tm_a, full_leader, sa, kb * BK, m0);
           tma_load_2d_pair(&tm_b, full_leader, sa + A_BYTES, kb * BK, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer (one lane of the leader CTA)
-    if (leader && lane == 0) {
-      const uint32_t idesc = p.idesc;
+    // ------------------------------------------------ MMA issuer (leader CTA; whole warp loops, one elected lane issues)
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      constexpr uint64_t desc_hi = umma_desc_sw128_hi();
+      const uint32_t smem_lo = (smem_u32(smem) & 0x3FFFFu) >> 4;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = pair; t < total; t += n_pairs) {
@@ -173,18 +192,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t da = p.desc_hi | static_cast<uint64_t>((a_addr & 0x3FFFFu) >> 4);
-          const uint64_t db = p.desc_hi | static_cast<uint64_t>(((a_addr + A_BYTES) & 0x3FFFFu) >> 4);
+          if (elect_one()) {
+            const uint32_t a_lo = smem_lo + stage * (STAGE_BYTES >> 4);
+            const uint64_t da = desc_hi | a_lo;
+            const uint64_t db = desc_hi | (a_lo + (A_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < BK / UK; ++k) {
-            // +32 B per K=16 slice inside the 128 B swizzle row (start address is in 16 B units)
-            tc_mma_bf16_pair(d_tmem, da + p.k_adv * k, db + p.k_adv * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / UK; ++k) {
+              // +32 B per K=16 slice inside the 128 B swizzle row (start address is in 16 B units)
+              tc_mma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            }
+            tc_commit_pair(&empty_bar[stage], 0x3);   // both CTAs' slots reusable once these MMAs retire
+            if (kb == k_blocks - 1) tc_commit_pair(&tfull_bar[acc], 0x3);   // accumulator complete in both CTAs
           }
-          tc_commit_pair(&empty_bar[stage], 0x3);   // both CTAs' slots reusable once these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit_pair(&tfull_bar[acc], 0x3);       // accumulator complete in both CTAs
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -259,9 +281,6 @@ int make_map(CUtensorMap* tm, const void* ptr, int rows, int K, int box_rows) {
 }
 
 int g_num_sms = 0;
-// bring-up overrides (vc_debug_gemm_override); 0 = built-in encoding
-uint64_t g_dbg_desc_hi = 0;
-uint32_t g_dbg_k_adv = 0, g_dbg_idesc = 0;
 std::mutex g_cfg_mu;
 bool g_attr_set[8] = {false};
 
@@ -285,10 +304,6 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
 
 }  // namespace
 
-void gemm_debug_override(uint64_t desc_hi, uint32_t k_adv, uint32_t idesc) {
-  g_dbg_desc_hi = desc_hi; g_dbg_k_adv = k_adv; g_dbg_idesc = idesc;
-}
-
 int gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int K, int mode, void* out, int ldo,
               const float* aux, int rows_per_group, int max_ctas, cudaStream_t stream) {
   VC_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
@@ -306,10 +321,7 @@ int gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int
   CUtensorMap ta, tb;
   if (int e = make_map(&ta, A, M, K, BM)) return e;
   if (int e = make_map(&tb, W, N, K, BN / 2)) return e;
-  GemmParams p{M, N, K, mode, bias, out, ldo, aux, rows_per_group,
-               g_dbg_desc_hi ? g_dbg_desc_hi : umma_desc_sw128_hi(),
-               g_dbg_k_adv ? g_dbg_k_adv : 2u,
-               g_dbg_idesc ? g_dbg_idesc : umma_idesc_bf16(2 * BM, BN)};
+  GemmParams p{M, N, K, mode, bias, out, ldo, aux, rows_per_group};
   const int total = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);   // pair tiles
   int pairs = g_num_sms / 2;
   if (total < pairs) pairs = total;

@@ -23,7 +23,6 @@ struct KernelScope {
 int gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int K, int mode, void* out, int ldo,
               const float* aux, int rows_per_group, int max_ctas, cudaStream_t stream);
 
-void gemm_debug_override(uint64_t desc_hi, uint32_t k_adv, uint32_t idesc);
 
 // vit_kernels.cu
 int preprocess_u8(const uint8_t* frames, const float* lut, void* out, int n, int H, int W, int layout, int patch, int k_pad,
@@ -34,6 +33,9 @@ int layernorm_f32_bf16(const float* x, const float* g, const float* b, void* out
 // fp32 rows picked with a stride (class tokens / last positions): out = LN(x[r*row_stride + row_offset])
 int layernorm_rows(const float* x, long long row_stride, long long row_offset, const float* g, const float* b, float* out_f32,
                    void* out_bf16, int rows, int dim, float eps, cudaStream_t s);
+// x[r] += delta[r] (bf16, may be null) in place, then out = LN(x[r]) for r = i*row_stride + row_offset
+int add_layernorm_rows(float* x, const void* delta_bf16, long long row_stride, long long row_offset, const float* g, const float* b,
+                       float* out_f32, void* out_bf16, int rows, int dim, float eps, cudaStream_t s);
 int vit_attention(const void* qkv, void* out, int n_frames, int tokens, int heads, int head_dim, cudaStream_t s);
 int cls_rows_init(float* x, const float* cls_pos0, int n_frames, int tokens, int dim, cudaStream_t s);
 int pool_prefix(const float* cls, int B, int T, int dim, const float* head_w, const float* head_b, int video_dim,

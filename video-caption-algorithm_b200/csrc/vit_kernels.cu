@@ -147,18 +147,26 @@ int preprocess_u8(const uint8_t* frames, const float* lut, void* out, int n, int
   return 0;
 }
 
-// =========================================================================== LayerNorm
-// One warp per row, fp32 in, two-pass statistics in registers, bf16 and/or fp32 out.
+// =========================================================================== (residual add +) LayerNorm
+// One warp per row, fp32 residual stream, two-pass statistics in registers, bf16 and/or fp32 out.
+// With `delta` (bf16 [rows_total, dim], the bias-added output of the preceding proj / fc2 GEMM) the kernel first
+// folds it into the residual stream: x += delta (written back in fp32), then normalises.  That is the
+// reference's `x = x + attn(...)` / `x + mlp(...)` (torchvision EncoderBlock.forward, timm Block.forward;
+// src/models/video_encoder.py:168-171) with the Linear output in bf16 exactly as under autocast, and it keeps
+// the GEMM epilogue write-only: a read-modify-write of the fp32 stream inside the epilogue made the
+// N=768,K=768 projection latency-bound (250-420 TFLOP/s).
 constexpr int LN_MAX_V4 = 8;   // dim <= 1024
 
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long row_stride, long long row_offset,
-                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+__global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delta, long long row_stride,
+                                                        long long row_offset, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
                                                         int rows, int dim, float eps) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
-  const float4* src = reinterpret_cast<const float4*>(x + (static_cast<long long>(warp) * row_stride + row_offset) * dim);
+  const long long in_row = static_cast<long long>(warp) * row_stride + row_offset;
+  float4* src = reinterpret_cast<float4*>(x + in_row * dim);
+  const uint2* dsrc = delta ? reinterpret_cast<const uint2*>(delta + in_row * dim) : nullptr;
   const int nv = dim >> 7;   // float4 per lane
   float4 v[LN_MAX_V4];
   float sum = 0.f;
@@ -166,6 +174,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   for (int i = 0; i < LN_MAX_V4; ++i)
     if (i < nv) {
       v[i] = src[i * 32 + lane];
+      if (dsrc != nullptr) {
+        const uint2 d = dsrc[i * 32 + lane];
+        const float2 a = unpack_bf16(d.x), b = unpack_bf16(d.y);
+        v[i].x += a.x; v[i].y += a.y; v[i].z += b.x; v[i].w += b.y;
+        src[i * 32 + lane] = v[i];
+      }
       sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
   const float mean = warp_sum(sum) / static_cast<float>(dim);
@@ -199,17 +213,22 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     }
 }
 
-int layernorm_rows(const float* x, long long row_stride, long long row_offset, const float* g, const float* b, float* out_f32,
-                   void* out_bf16, int rows, int dim, float eps, cudaStream_t s) {
+int add_layernorm_rows(float* x, const void* delta_bf16, long long row_stride, long long row_offset, const float* g, const float* b,
+                       float* out_f32, void* out_bf16, int rows, int dim, float eps, cudaStream_t s) {
   VC_REQUIRE(dim % 128 == 0 && dim <= 128 * LN_MAX_V4, "layernorm: dim=%d must be a multiple of 128 and <= %d", dim,
              128 * LN_MAX_V4);
   if (rows <= 0) return 0;
   const int grid = (rows + 7) / 8;
-  VC_LAUNCH("layernorm", static_cast<double>(rows) * dim * 6.0, s,
-            (layernorm_kernel<<<grid, 256, 0, s>>>(x, row_stride, row_offset, g, b, out_f32,
+  VC_LAUNCH(delta_bf16 ? "add_layernorm" : "layernorm", static_cast<double>(rows) * dim * (delta_bf16 ? 12.0 : 6.0), s,
+            (layernorm_kernel<<<grid, 256, 0, s>>>(x, static_cast<const __nv_bfloat16*>(delta_bf16), row_stride, row_offset, g, b, out_f32,
                                                    static_cast<__nv_bfloat16*>(out_bf16), rows, dim, eps)));
   VC_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+int layernorm_rows(const float* x, long long row_stride, long long row_offset, const float* g, const float* b, float* out_f32,
+                   void* out_bf16, int rows, int dim, float eps, cudaStream_t s) {
+  return add_layernorm_rows(const_cast<float*>(x), nullptr, row_stride, row_offset, g, b, out_f32, out_bf16, rows, dim, eps, s);
 }
 
 int layernorm_f32_bf16(const float* x, const float* g, const float* b, void* out, int rows, int dim, float eps, cudaStream_t s) {

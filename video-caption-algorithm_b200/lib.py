@@ -96,7 +96,6 @@ _SIGNATURES = {
     "vc_preprocess_u8": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "vc_patchify_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "vc_gemm_bf16": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p]),
-    "vc_debug_gemm_override": (None, [C.c_ulonglong, C.c_uint, C.c_uint]),
     "vc_layernorm_f32_bf16": (_i, [_p, _p, _p, _p, _i, _i, _f, _p]),
     "vc_vit_attention": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "vc_vit_workspace_bytes": (_sz, [C.POINTER(VcVitWeights), _i]),
