@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -76,9 +77,10 @@ static VitBuffers carve_vit(const VcVitWeights* w, int chunk_frames, void* base)
 
 struct GptBuffers {
   float* h; void* xn; void* qkv; void* att; void* hid; float* emb; float* logits; int32_t* finished; int32_t* next; float* partial;
+  float* cand_v; int* cand_i; unsigned int* bar;
   size_t total;
 };
-constexpr int kSkinnyMaxRows = 128;   // decode steps with more live sequences use the tcgen05 GEMM
+constexpr int kDecodeMaxRows = 128;   // decode steps with more live sequences use the tcgen05 GEMM path
 static GptBuffers carve_gpt(const VcGptWeights* w, int n_seq, int max_rows, void* base) {
   const size_t R = static_cast<size_t>(max_rows);
   uint8_t* p = static_cast<uint8_t*>(base);
@@ -94,13 +96,18 @@ static GptBuffers carve_gpt(const VcGptWeights* w, int n_seq, int max_rows, void
   b.finished = reinterpret_cast<int32_t*>(p + off); off += align_up(static_cast<size_t>(n_seq) * 4, 1024);
   b.next = reinterpret_cast<int32_t*>(p + off);     off += align_up(static_cast<size_t>(n_seq) * 4, 1024);
   {
-    // split-K partials of the skinny decode GEMMs: the widest of the four per-layer products
-    const int H = w->dim, rows = n_seq < kSkinnyMaxRows ? n_seq : kSkinnyMaxRows;
-    size_t m = static_cast<size_t>(skinny_ksplit(3 * H, H)) * 3 * H;
+    // fp32 split-K partials of the decode step's GEMMs (widest product), per-CTA argmax candidates, grid barrier
+    const size_t rows = n_seq < kDecodeMaxRows ? n_seq : kDecodeMaxRows;
+    const int H = w->dim;
+    size_t m = decode_partial_floats_per_row(w);
+    m = std::max(m, static_cast<size_t>(skinny_ksplit(3 * H, H)) * 3 * H);
     m = std::max(m, static_cast<size_t>(skinny_ksplit(H, H)) * H);
     m = std::max(m, static_cast<size_t>(skinny_ksplit(4 * H, H)) * 4 * H);
     m = std::max(m, static_cast<size_t>(skinny_ksplit(H, 4 * H)) * H);
     b.partial = reinterpret_cast<float*>(p + off);  off += align_up(m * rows * 4, 1024);
+    b.cand_v = reinterpret_cast<float*>(p + off);   off += align_up(static_cast<size_t>(256) * 128 * 4, 1024);
+    b.cand_i = reinterpret_cast<int*>(p + off);     off += align_up(static_cast<size_t>(256) * 128 * 4, 1024);
+    b.bar = reinterpret_cast<unsigned int*>(p + off); off += 1024;
   }
   b.total = off;
   return b;
@@ -237,8 +244,9 @@ int vc_linear_bias_f32(const float* x, const float* w, const float* b, float* y,
 
 size_t vc_gpt_workspace_bytes(const VcGptWeights* w, int n_seq, int max_new_rows) { return carve_gpt(w, n_seq, max_new_rows, nullptr).total; }
 
-// Decode step (one new position per sequence, few rows): every product streams its weights once
-// through the skinny split-K kernel; partial sums are folded into the next kernel of the chain.
+// Decode step as a chain of small kernels (one new position per sequence, few rows): every product streams its weights
+// once through the split-K skinny kernel, partial sums are folded into the next kernel of the chain, and every kernel is
+// a programmatic dependent launch so its launch latency and ramp overlap the previous kernel's tail.
 static int gpt_step_skinny(const VcGptWeights* w, const float* embeds, int n_seq, int past_len, VcKvCache* cache, const GptBuffers& b,
                            float* logits_out, cudaStream_t s) {
   const int H = w->dim, M = n_seq;
@@ -264,11 +272,25 @@ static int gpt_step_skinny(const VcGptWeights* w, const float* embeds, int n_seq
   return skinny_gemm(b.xn, w->wte, logits_out, M, w->vocab_pad, H, 1, s);
 }
 
+// VC_DECODE_PERSISTENT=1 selects the single-launch cooperative decode kernel (decode_step.cu); measured on B200 it is
+// device-barrier bound (~86 barriers x ~4.5 us per step) and not yet faster than the PDL kernel chain, which is the default.
+static bool use_persistent_decode() {
+  static const bool on = getenv("VC_DECODE_PERSISTENT") != nullptr && getenv("VC_DECODE_PERSISTENT")[0] == '1';
+  return on;
+}
+
+static DecodeBuffers decode_buffers(const GptBuffers& b) {
+  return DecodeBuffers{b.h, b.xn, b.att, b.hid, b.partial, b.cand_v, b.cand_i, b.bar};
+}
+
 static int gpt_forward_impl(const VcGptWeights* w, const float* embeds, int n_seq, int L, int past_len, VcKvCache* cache,
                             const GptBuffers& b, float* logits_out, cudaStream_t s) {
   const int H = w->dim, M = n_seq * L;
   int e;
-  if (L == 1 && n_seq <= kSkinnyMaxRows && w->vocab_pad % 64 == 0) return gpt_step_skinny(w, embeds, n_seq, past_len, cache, b, logits_out, s);
+  // one new position per sequence
+  if (L == 1 && past_len >= 1 && use_persistent_decode() && decode_supported(w, n_seq, cache))
+    return decode_steps(w, decode_buffers(b), cache, n_seq, past_len, 1, embeds, nullptr, logits_out, 0, s);
+  if (L == 1 && n_seq <= kDecodeMaxRows && w->vocab_pad % 64 == 0) return gpt_step_skinny(w, embeds, n_seq, past_len, cache, b, logits_out, s);
   if ((e = gpt_add_pos(embeds, w->wpe, b.h, n_seq, L, past_len, H, s))) return e;
   for (int l = 0; l < w->layers; ++l) {
     const VcGptLayer& Ly = w->layer[l];
@@ -317,10 +339,17 @@ int vc_greedy_decode(const VcGptWeights* w, const float* prefix, int n_seq, int 
   int e;
   if ((e = greedy_init(ids_out, len_out, b.finished, n_seq, max_new, eos, s))) return e;
   if ((e = build_prefill_embeds(prefix, w->wte, prompt_ids, n_seq, P, Lp, w->dim, b.emb, s))) return e;
+  const bool fused = max_new > 1 && use_persistent_decode() && decode_supported(w, n_seq, cache);
   for (int step = 0; step < max_new; ++step) {
     const int L = step == 0 ? L0 : 1;
     const int past = step == 0 ? 0 : L0 + step - 1;
     float* lg = step_logits ? step_logits + static_cast<size_t>(step) * n_seq * w->vocab_pad : b.logits;
+    if (step == 1 && fused) {
+      // steps 1..max_new-1 (argmax, bookkeeping and token feedback included) in ONE persistent launch
+      DecodeGreedy g{1, max_new, eos, b.finished, ids_out, len_out, forced_ids, b.next};
+      return decode_steps(w, decode_buffers(b), cache, n_seq, past, max_new - 1, b.emb, &g, step_logits ? lg : nullptr,
+                          static_cast<long long>(n_seq) * w->vocab_pad, s);
+    }
     if ((e = gpt_forward_impl(w, b.emb, n_seq, L, past, cache, b, lg, s))) return e;
     const bool last = step == max_new - 1;
     if ((e = greedy_select(lg, w->vocab_pad, w->vocab, n_seq, step, max_new, eos, b.finished, ids_out, len_out, forced_ids, w->wte,

@@ -27,6 +27,8 @@
 
 namespace vc {
 
+int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* ptr, int rows, int K, int box_rows);
+
 namespace {
 
 constexpr int BM = 128;                // rows of A per CTA; a pair covers 256
@@ -264,21 +266,7 @@ int get_encode() {
   return g_encode ? 0 : -1;
 }
 
-// K-major bf16 [rows, K] matrix, box = [BK, box_rows], 128-byte swizzle.
-int make_map(CUtensorMap* tm, const void* ptr, int rows, int K, int box_rows) {
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ptr=%p", static_cast<int>(r), rows, K, ptr);
-    return -3;
-  }
-  return 0;
-}
+int make_map(CUtensorMap* tm, const void* ptr, int rows, int K, int box_rows) { return make_tmap_bf16_kmajor(tm, ptr, rows, K, box_rows); }
 
 int g_num_sms = 0;
 std::mutex g_cfg_mu;
@@ -303,6 +291,23 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
 }
 
 }  // namespace
+
+// K-major bf16 [rows, K] matrix, box = [64, box_rows], 128-byte swizzle (shared with the decode kernel).
+int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* ptr, int rows, int K, int box_rows) {
+  VC_REQUIRE(get_encode() == 0, "cuTensorMapEncodeTiled entry point not found (no CUDA driver?)");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%d K=%d box_rows=%d ptr=%p", static_cast<int>(r), rows, K, box_rows, ptr);
+    return -3;
+  }
+  return 0;
+}
 
 int gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int K, int mode, void* out, int ldo,
               const float* aux, int rows_per_group, int max_ctas, cudaStream_t stream) {

@@ -19,6 +19,8 @@ namespace vc {
 // h[s, l, :] = embeds[s, l, :] + wpe[past_len + l, :]     (GPT2Model.forward: inputs_embeds + position_embeds)
 __global__ void add_pos_kernel(const float* __restrict__ e, const float* __restrict__ wpe, float* __restrict__ h, int n_seq, int L,
                                int past_len, int dim4) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(n_seq) * L * dim4;
   if (i >= total) return;
@@ -33,7 +35,8 @@ int gpt_add_pos(const float* embeds, const float* wpe, float* h, int n_seq, int 
   const long long total = static_cast<long long>(n_seq) * L * (dim / 4);
   if (total == 0) return 0;
   VC_LAUNCH("gpt_add_pos", total * 32.0, s,
-            (add_pos_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(embeds, wpe, h, n_seq, L, past_len, dim / 4)));
+            VC_CUDA_OK(launch_pdl(add_pos_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, embeds, wpe, h, n_seq, L, past_len,
+                                  dim / 4)));
   VC_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -67,6 +70,8 @@ __global__ void __launch_bounds__(128) gpt_attention_kernel(const __nv_bfloat16*
                                                             __nv_bfloat16* __restrict__ kv, const int32_t* __restrict__ slot,
                                                             int layer, int n_seq, int rows_total, int heads, int s_max, int L, int past_len) {
   __shared__ float s_p[4][ATT_MAX_S];
+  pdl_wait();
+  pdl_launch_dependents();
   const int seq = blockIdx.x / heads, head = blockIdx.x - seq * heads;
   const int H = heads * GHD;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -150,6 +155,8 @@ __global__ void __launch_bounds__(128) gpt_attention_smem_kernel(const __nv_bflo
                                                                  int n_seq, int rows_total, int heads, int s_max, int L, int past_len) {
   extern __shared__ __align__(16) uint8_t s_kv[];            // K rows then V rows, ATT_ROW_B bytes each
   __shared__ float s_p[4][ATT_SMEM_MAX_S];
+  pdl_wait();
+  pdl_launch_dependents();
   const int seq = blockIdx.x / heads, head = blockIdx.x - seq * heads;
   const int H = heads * GHD;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -248,16 +255,17 @@ int gpt_attention(const void* qkv, const float* P, int ksplit, const float* bias
       attr = ATT_SMEM_MAX_S * (2 * ATT_ROW_B + GHD * 4);
     }
     VC_LAUNCH("gpt_attention", bytes, s,
-              (gpt_attention_smem_kernel<<<n_seq * c->heads, 128, smem, s>>>(static_cast<const __nv_bfloat16*>(qkv), P, ksplit, bias,
-                                                                         static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(c->kv),
-                                                                         c->slot, layer, c->n_seq, n_seq * L, c->heads, c->s_max, L, past_len)));
+              VC_CUDA_OK(launch_pdl(gpt_attention_smem_kernel, dim3(n_seq * c->heads), dim3(128), static_cast<size_t>(smem), s,
+                                    static_cast<const __nv_bfloat16*>(qkv), P, ksplit, bias, static_cast<__nv_bfloat16*>(out),
+                                    static_cast<__nv_bfloat16*>(c->kv), static_cast<const int32_t*>(c->slot), layer, c->n_seq, n_seq * L, c->heads,
+                                    c->s_max, L, past_len)));
     VC_CUDA_OK(cudaGetLastError());
     return 0;
   }
   VC_LAUNCH("gpt_attention", bytes, s,
-            (gpt_attention_kernel<<<n_seq * c->heads, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), P, ksplit, bias,
-                                                                  static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(c->kv), c->slot,
-                                                                  layer, c->n_seq, n_seq * L, c->heads, c->s_max, L, past_len)));
+            VC_CUDA_OK(launch_pdl(gpt_attention_kernel, dim3(n_seq * c->heads), dim3(128), 0, s, static_cast<const __nv_bfloat16*>(qkv), P, ksplit, bias,
+                                  static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(c->kv), static_cast<const int32_t*>(c->slot), layer,
+                                  c->n_seq, n_seq * L, c->heads, c->s_max, L, past_len)));
   VC_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -368,6 +376,8 @@ __global__ void __launch_bounds__(1024) greedy_select_kernel(const float* __rest
                                                              int32_t* __restrict__ len_out, const int32_t* __restrict__ forced,
                                                              const __nv_bfloat16* __restrict__ wte, int dim, float* __restrict__ next_embeds,
                                                              int32_t* __restrict__ next_ids) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int r = blockIdx.x;
   int tok = block_argmax(logits + r * ld, vocab);
   const bool was_finished = finished[r] != 0;
@@ -390,8 +400,8 @@ int greedy_select(const float* logits, long long ld, int vocab, int n_seq, int s
                   int32_t* next_ids, cudaStream_t s) {
   if (n_seq <= 0) return 0;
   VC_LAUNCH("greedy_select", static_cast<double>(n_seq) * vocab * 4.0, s,
-            (greedy_select_kernel<<<n_seq, 1024, 0, s>>>(logits, ld, vocab, step, max_new, eos, finished, ids_out, len_out, forced,
-                                                         static_cast<const __nv_bfloat16*>(wte), dim, next_embeds, next_ids)));
+            VC_CUDA_OK(launch_pdl(greedy_select_kernel, dim3(n_seq), dim3(1024), 0, s, logits, ld, vocab, step, max_new, eos, finished, ids_out, len_out,
+                                  forced, static_cast<const __nv_bfloat16*>(wte), dim, next_embeds, next_ids)));
   VC_CUDA_OK(cudaGetLastError());
   return 0;
 }

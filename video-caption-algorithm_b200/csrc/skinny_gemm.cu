@@ -49,6 +49,8 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
 // grid = (N/64, ksplit, ceil(M/64)), block = 128
 __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ W,
                                                                    float* __restrict__ P, int M, int N, int K, int kslice) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int f0 = blockIdx.x * SK_BN + warp * 16;
@@ -133,6 +135,8 @@ __global__ void __launch_bounds__(256) resid_ln_kernel(float* __restrict__ h, co
                                                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ xn, int rows, int dim,
                                                        float eps) {
   __shared__ float s_red[8];
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x, c4 = threadIdx.x;          // blockDim.x == dim / 4
   const size_t plane4 = static_cast<size_t>(rows) * dim / 4;
   const size_t o4 = static_cast<size_t>(row) * (dim / 4) + c4;
@@ -167,6 +171,8 @@ __global__ void __launch_bounds__(256) resid_ln_kernel(float* __restrict__ h, co
 // out[m][n] = bf16(act(bias[n] + sum_s P[s][m][n]))
 __global__ void __launch_bounds__(256) bias_act_kernel(const float* __restrict__ P, int ksplit, const float* __restrict__ bias,
                                                        __nv_bfloat16* __restrict__ out, int M, int N, int gelu) {
+  pdl_wait();
+  pdl_launch_dependents();
   const size_t i4 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const size_t total4 = static_cast<size_t>(M) * N / 4;
   if (i4 >= total4) return;
@@ -204,8 +210,8 @@ int skinny_gemm(const void* x, const void* W, float* P, int M, int N, int K, int
   VC_REQUIRE(ksplit >= 1 && (K / SK_KB) % ksplit == 0, "skinny_gemm: ksplit=%d does not divide K/64=%d", ksplit, K / SK_KB);
   dim3 grid(N / SK_BN, ksplit, (M + SK_MT - 1) / SK_MT);
   VC_LAUNCH("skinny_gemm", static_cast<double>(N) * K * 2.0, s,
-            (skinny_gemm_kernel<<<grid, SK_WARPS * 32, 0, s>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(W), P, M,
-                                                              N, K, K / ksplit)));
+            VC_CUDA_OK(launch_pdl(skinny_gemm_kernel, grid, dim3(SK_WARPS * 32), 0, s, static_cast<const __nv_bfloat16*>(x),
+                                  static_cast<const __nv_bfloat16*>(W), P, M, N, K, K / ksplit)));
   VC_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -215,7 +221,8 @@ int resid_ln(float* h, const float* P, int ksplit, const float* bias, const floa
   VC_REQUIRE(dim % 128 == 0 && dim <= 1024 && ksplit <= RL_MAX_KS, "resid_ln: dim=%d ksplit=%d", dim, ksplit);
   if (rows <= 0) return 0;
   VC_LAUNCH("resid_ln", static_cast<double>(rows) * dim * (10.0 + 4.0 * ksplit), s,
-            (resid_ln_kernel<<<rows, dim / 4, 0, s>>>(h, P, ksplit, bias, gamma, beta, static_cast<__nv_bfloat16*>(xn), rows, dim, eps)));
+            VC_CUDA_OK(launch_pdl(resid_ln_kernel, dim3(rows), dim3(dim / 4), 0, s, h, P, ksplit, bias, gamma, beta, static_cast<__nv_bfloat16*>(xn),
+                                  rows, dim, eps)));
   VC_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -225,7 +232,8 @@ int bias_act(const float* P, int ksplit, const float* bias, void* out, int M, in
   const size_t total4 = static_cast<size_t>(M) * N / 4;
   if (total4 == 0) return 0;
   VC_LAUNCH("bias_act", static_cast<double>(M) * N * (2.0 + 4.0 * ksplit), s,
-            (bias_act_kernel<<<static_cast<int>((total4 + 255) / 256), 256, 0, s>>>(P, ksplit, bias, static_cast<__nv_bfloat16*>(out), M, N, gelu)));
+            VC_CUDA_OK(launch_pdl(bias_act_kernel, dim3(static_cast<unsigned>((total4 + 255) / 256)), dim3(256), 0, s, P, ksplit, bias,
+                                  static_cast<__nv_bfloat16*>(out), M, N, gelu)));
   VC_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -77,6 +77,13 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   return 0.5f * x * (1.0f + tanhf(u));
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Kernels of the decode-step chain start with pdl_wait(): when launched with the programmatic-stream-serialization
+// attribute their CTAs are scheduled while the previous kernel is still draining (launch latency and ramp hidden) and
+// block here until that kernel has completed and flushed; without the attribute it is a no-op.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

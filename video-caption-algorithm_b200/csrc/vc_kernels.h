@@ -19,6 +19,18 @@ struct KernelScope {
   int slot_;
 };
 
+// Launch with the programmatic-stream-serialization attribute (the kernel must begin with pdl_wait()).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // gemm_tcgen05.cu
 int gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int K, int mode, void* out, int ldo,
               const float* aux, int rows_per_group, int max_ctas, cudaStream_t stream);
@@ -65,6 +77,22 @@ int greedy_select(const float* logits, long long ld, int vocab, int n_seq, int s
                   int32_t* next_ids, cudaStream_t s);
 int build_prefill_embeds(const float* prefix, const void* wte_bf16, const int32_t* prompt_ids, int n_seq, int P, int Lp,
                          int dim, float* out, cudaStream_t s);
+
+// decode_step.cu — persistent cooperative decode kernel (n_seq <= 128)
+struct DecodeBuffers {
+  float* h; void* xn; void* att; void* hid; float* part; float* cand_v; int* cand_i; unsigned int* bar;
+};
+struct DecodeGreedy {
+  int step0, max_new, eos;
+  int32_t* finished; int32_t* ids_out; int32_t* len_out; const int32_t* forced; int32_t* next_ids;
+};
+bool decode_supported(const VcGptWeights* w, int n_seq, const VcKvCache* c);
+size_t decode_partial_floats_per_row(const VcGptWeights* w);
+// n_steps decode steps starting with input embeddings `emb` (fp32 [n_seq,H], no position) at position past0.
+// greedy != null: argmax + benchmark bookkeeping + feedback on device, steps step0..step0+n_steps-1;
+// greedy == null: one forward step, logits (fp32 [n_seq, vocab_pad]) required.
+int decode_steps(const VcGptWeights* w, const DecodeBuffers& b, const VcKvCache* cache, int n_seq, int past0, int n_steps, const float* emb,
+                 const DecodeGreedy* greedy, float* logits, long long logits_step_stride, cudaStream_t stream);
 
 // beam_kernels.cu
 int beam_step(const float* logits, long long ld, int vocab, int n_rows, int rows_per_item, const int32_t* seqs, int max_len, int cur_len,

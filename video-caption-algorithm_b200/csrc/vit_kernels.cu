@@ -161,6 +161,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, c
                                                         long long row_offset, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
                                                         int rows, int dim, float eps) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
