@@ -7,6 +7,7 @@
 #include "vc_common.cuh"
 #include "vc_kernels.h"
 #include <algorithm>
+#include <cstdlib>
 
 namespace vc {
 
@@ -426,6 +427,10 @@ int vit_attention(const void* qkv, void* out, int n_frames, int tokens, int head
   VC_REQUIRE(head_dim == HD, "vit_attention: head_dim=%d (only 64 is built)", head_dim);
   VC_REQUIRE(tokens > 0 && tokens <= 576, "vit_attention: tokens=%d out of range", tokens);
   if (n_frames <= 0) return 0;
+  // tokens <= 256 (ViT-B/16: 197): the tcgen05 kernel; longer sequences (ViT-L/14: 257) stay on the mma.sync kernel below
+  static const bool legacy = getenv("VC_VIT_ATTENTION_MMA_SYNC") != nullptr;
+  if (!legacy && vit_attention_tc_supported(tokens, heads, head_dim) && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0)
+    return vit_attention_tc(qkv, out, n_frames, tokens, heads, s);
   const int s_pad = ((tokens + 63) / 64) * 64;
   const int smem = 3 * s_pad * 128;
   static int attr_smem = 0;
