@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="videos per GPU")
     ap.add_argument("--frames", type=int, default=16)
     ap.add_argument("--max-new", type=int, default=20)
-    ap.add_argument("--chunk-frames", type=int, default=int(os.environ.get("VC_CHUNK_FRAMES", "256")))
+    ap.add_argument("--chunk-frames", type=int, default=int(os.environ.get("VC_CHUNK_FRAMES", "1024")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -197,15 +197,19 @@ def run_b200(args):
     from vcb200.sharding import gather_ids, shard_range
     assert shard_range(world * B, world, rank) == (rank * B, rank * B + B)
 
-    def step_resident():
-        ids, lens = model.caption_ids(dev_frames, max_new_tokens=n_new)
+    # The timed path is the three-stream pipeline (model.pipeline): H2D of batch i+2, encode of batch i+1 and decode of
+    # batch i overlap; every batch still runs preprocess -> ViT -> prefix -> 20 greedy steps -> (gather) in full.
+    pipe = model.pipeline(max_new_tokens=n_new)
+
+    def after_decode(ids, lens):
         if world > 1:
             gather_ids(ids, lens, world * B)        # the path's only exchange: token ids (+lengths) over NVLink
-        return ids, lens
+
+    def step_resident():
+        return pipe.submit(dev_frames, to_host=False, after_decode=after_decode)
 
     def step_e2e():
-        ids, lens = model.caption_from_host(host_frames, max_new_tokens=n_new)   # H2D + pipeline + D2H
-        return ids, lens
+        return pipe.submit(host_frames, to_host=True, after_decode=after_decode)   # pinned H2D + pipeline + ids D2H
 
     def barrier():
         if world > 1:
@@ -216,8 +220,11 @@ def run_b200(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        for s_ in (pipe.copy_stream, pipe.enc_stream, pipe.dec_stream):
+            s_.wait_event(e0)
         for _ in range(steps):
             out = fn()
+        torch.cuda.current_stream().wait_event(pipe.last_event())     # the last batch's decode (+gather, +D2H) has finished
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -241,8 +248,9 @@ def run_b200(args):
 
     l0 = lib.vc_launch_count()
     sampler.mark_begin()
-    ms, (ids, lens) = timed(step_resident, args.steps)
+    ms, ticket = timed(step_resident, args.steps)
     sampler.mark_end()
+    ids, lens = pipe.result(ticket, host=False)
     live = lib.vc_launch_count() - l0
     clocks = sampler.stop()
     launches = live + args.steps * graph_nodes
@@ -319,9 +327,10 @@ def run_b200(args):
                                    f"(BASELINE.json configs[1]; configs[2] layout at N>1), random-init weights",
                        "videos_per_gpu": B, "global_batch": world * B, "frames": T, "max_new_tokens": n_new,
                        "parallelism": f"videos sharded over {world} GPU(s), ids all_gather", "chunk_frames": args.chunk_frames,
+                       "pipelining": "batches back to back on 3 streams (H2D / encode / decode overlap across batches); stages_ms is one batch alone",
                        "l2": "inputs (154 MB uint8 frames) and per-layer activations (>300 MB) exceed the 126 MB L2 every step"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": roofline, "decode": decode,
+            "roofline": roofline, "decode": decode, "single_batch_ms": round(enc_ms + dec_ms, 3),
             "stages_ms": {"preprocess+ViT_Encoder+Cross_Modal_Alignment": round(enc_ms, 3), "GPT2_Decoder_Step(x%d)" % n_new: round(dec_ms, 3)},
             "kernels_one_encoder_pass": kern,
             "sample_ids": ids[0, :8].tolist(),

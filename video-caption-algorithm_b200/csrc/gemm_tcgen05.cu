@@ -4,7 +4,7 @@
 //     stages its 128 rows of A and its 128 rows of W per 64-wide K block, so a pair moves 64 KB
 //     per 8.4 MFLOP (128 flop/B) instead of the 85 flop/B of a single-CTA 128x256 tile — the
 //     L2->SM fill rate, not the tensor pipe, was the limit of the single-CTA version;
-//   * operands staged by TMA (cp.async.bulk.tensor, SWIZZLE_128B) through a 6-deep mbarrier
+//   * operands staged by TMA (cp.async.bulk.tensor, SWIZZLE_128B) through a 4-deep mbarrier
 //     ring; both CTAs' loads complete on the leader's "full" barrier, the MMA's tcgen05.commit
 //     multicasts the "empty" arrive to both CTAs;
 //   * one elected thread of the leader CTA issues tcgen05.mma (M=256, N=256, K=16); fp32
@@ -22,6 +22,7 @@
 #include "vc_kernels.h"
 
 #include <cudaTypedefs.h>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -34,7 +35,10 @@ namespace {
 constexpr int BM = 128;                // rows of A per CTA; a pair covers 256
 constexpr int BN = 256;                // columns per pair tile; each CTA stages BN/2 rows of W
 constexpr int BK = 64, UK = 16;
-constexpr int STAGES = 6;
+// 4 stages measure the same as 6 on every ViT shape (the ring only has to cover the L2 latency), and 161 KB instead of
+// 225 KB of shared memory leaves room on each SM for the small decode-step kernels of the PREVIOUS batch to run
+// underneath the encoder GEMMs of the next one (model.py: CaptionPipeline).
+constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;          // 16 KB
 constexpr int B_BYTES = (BN / 2) * BK * 2;    // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -328,7 +332,9 @@ int gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int
   if (int e = make_map(&tb, W, N, K, BN / 2)) return e;
   GemmParams p{M, N, K, mode, bias, out, ldo, aux, rows_per_group};
   const int total = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);   // pair tiles
-  int pairs = g_num_sms / 2;
+  // VC_ENCODER_SMS=n leaves SMs free for kernels of another stream (the decode chain of the previous batch)
+  static const int sm_cap = getenv("VC_ENCODER_SMS") ? atoi(getenv("VC_ENCODER_SMS")) : 0;
+  int pairs = (sm_cap > 0 && sm_cap < g_num_sms ? sm_cap : g_num_sms) / 2;
   if (total < pairs) pairs = total;
   if (max_ctas > 0 && 2 * pairs > max_ctas) pairs = max_ctas / 2 > 0 ? max_ctas / 2 : 1;
   const int grid = 2 * pairs;

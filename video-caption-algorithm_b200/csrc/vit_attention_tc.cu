@@ -19,6 +19,7 @@
 #include "vc_kernels.h"
 
 #include <cudaTypedefs.h>
+#include <cstdlib>
 
 namespace vc {
 
@@ -306,7 +307,9 @@ int vit_attention_tc(const void* qkv, void* out, int n_frames, int tokens, int h
   if ((e = make_tmap_bf16_kmajor(&tkv, qkv, rows, 3 * D, NK))) return e;
   AttParams p{static_cast<__nv_bfloat16*>(out), n_frames, tokens, heads, D, NK, m_tiles};
   const int items = n_frames * heads;
-  const int grid = items < g_at_sms ? items : g_at_sms;
+  static const int sm_cap = getenv("VC_ENCODER_SMS") ? atoi(getenv("VC_ENCODER_SMS")) : 0;
+  const int sms = sm_cap > 0 && sm_cap < g_at_sms ? sm_cap : g_at_sms;
+  const int grid = items < sms ? items : sms;
   {
     KernelScope ks("vit_attention", 4.0 * n_frames * heads * static_cast<double>(tokens) * tokens * 64, s);
     vit_attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM, s>>>(tq, tkv, p);

@@ -54,7 +54,10 @@ def greedy_decode(m, prefix: torch.Tensor, prompt_ids: List[int], max_new: int, 
     st = _greedy_buffers(m, n_seq, L0, max_new, keep_logits)
     pre = st["prefix"].view(-1)[: n_seq * P * H].view(n_seq, P, H)
     pre.copy_(prefix.to(device=m.device, dtype=torch.float32))
-    st["prompt"][:Lp].copy_(torch.tensor(prompt_ids, dtype=torch.int32), non_blocking=False)
+    if st.get("prompt_host") != tuple(prompt_ids):          # H2D of the prompt ids only when they change
+        st["prompt"][:Lp].copy_(torch.tensor(prompt_ids, dtype=torch.int32), non_blocking=False)
+        torch.cuda.current_stream().synchronize()
+        st["prompt_host"] = tuple(prompt_ids)
     use_forced = forced_ids is not None
     if use_forced:
         st["forced"].copy_(forced_ids.to(device=m.device, dtype=torch.int32))
@@ -73,7 +76,10 @@ def greedy_decode(m, prefix: torch.Tensor, prompt_ids: List[int], max_new: int, 
         enqueue()                              # eager warm-up (also sets func attributes outside capture)
         torch.cuda.current_stream().synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # kernel nodes keep the priority of the stream they were captured on: capture on a high-priority stream so that the
+        # decode chain is scheduled ahead of the next batch's encoder CTAs when the two overlap (CaptionPipeline)
+        cap = torch.cuda.Stream(device=m.device, priority=-1)
+        with torch.cuda.graph(g, stream=cap):
             enqueue()
         st[gkey] = g
         g.replay()

@@ -289,6 +289,10 @@ class B200CaptionModel:
             torch.cuda.nvtx.range_pop()
         return ids, lengths
 
+    def pipeline(self, max_new_tokens: int = 20) -> "CaptionPipeline":
+        """Throughput path: a three-stream software pipeline over batches (see CaptionPipeline)."""
+        return CaptionPipeline(self, max_new_tokens)
+
     def caption_from_host(self, frames_u8_host: torch.Tensor, max_new_tokens: int = 20, num_beams: int = 1):
         """End-to-end call with HOST buffers: pinned uint8 frames -> H2D -> pipeline -> ids D2H.
         This is the public call bench.py's `e2e` figure times."""
@@ -296,3 +300,85 @@ class B200CaptionModel:
         dev_frames.copy_(frames_u8_host, non_blocking=True)
         ids, lengths = self.caption_ids(dev_frames, max_new_tokens, num_beams)
         return ids.cpu(), lengths.cpu()
+
+
+class CaptionPipeline:
+    """Batches in flight on three streams: H2D copy of batch i+2, preprocess + ViT encode + prefix of batch i+1, and the
+    greedy decode of batch i.  The decode step is a chain of ~100 tiny latency-bound kernels that needs a few SM slots,
+    the encoder is tensor-pipe bound; with the GEMM's shared-memory footprint cut to 161 KB the decode kernels of the
+    previous batch run underneath the encoder kernels of the next one (the decode stream has the higher priority), so
+    steady-state time per batch tends to the encoder time alone.  Results are bit-identical to `caption_ids`: the same
+    kernels run on the same data, only on different streams.
+
+        pipe = model.pipeline(max_new_tokens=20)
+        t0 = pipe.submit(frames0)      # uint8 [B,T,H,W,3]: device tensor, or pinned host tensor (copied asynchronously)
+        t1 = pipe.submit(frames1)
+        ids, lens = pipe.result(t0)    # host int32 tensors (pinned); blocks until that batch is done
+    """
+
+    DEPTH = 3
+
+    def __init__(self, model: B200CaptionModel, max_new_tokens: int):
+        self.m = model
+        self.max_new = int(max_new_tokens)
+        dev = model.device
+        with torch.cuda.device(dev):
+            self.copy_stream = torch.cuda.Stream(dev)
+            self.enc_stream = torch.cuda.Stream(dev)
+            self.dec_stream = torch.cuda.Stream(dev, priority=-1)
+        self._slots = [dict(frames=None, ids=None, lens=None, done=None, enc_done=None, h_ids=None, h_lens=None) for _ in range(self.DEPTH)]
+        self._n = 0
+
+    def submit(self, frames_u8: torch.Tensor, to_host: bool = True, after_decode=None) -> int:
+        m, ticket = self.m, self._n
+        slot = self._slots[ticket % self.DEPTH]
+        if slot["done"] is not None:
+            slot["done"].synchronize()                       # back-pressure: at most DEPTH batches in flight
+        B = frames_u8.shape[0]
+        if frames_u8.device.type == "cpu":
+            if slot["frames"] is None or slot["frames"].shape != frames_u8.shape:
+                slot["frames"] = torch.empty(frames_u8.shape, dtype=torch.uint8, device=m.device)
+            with torch.cuda.stream(self.copy_stream):
+                if slot["enc_done"] is not None:
+                    self.copy_stream.wait_event(slot["enc_done"])   # the encoder has finished reading this buffer
+                slot["frames"].copy_(frames_u8, non_blocking=True)
+                copied = self.copy_stream.record_event()
+            dev_frames = slot["frames"]
+        else:
+            copied, dev_frames = None, frames_u8
+        with torch.cuda.stream(self.enc_stream):
+            if copied is not None:
+                self.enc_stream.wait_event(copied)
+            feat, prefix = m.encode_prefix(dev_frames)
+            slot["enc_done"] = self.enc_stream.record_event()
+            prefix.record_stream(self.dec_stream)
+        with torch.cuda.stream(self.dec_stream):
+            self.dec_stream.wait_event(slot["enc_done"])
+            ids, lens, _ = m.greedy_ids(prefix, None, self.max_new)
+            if slot["ids"] is None or slot["ids"].shape != ids.shape:
+                slot["ids"], slot["lens"] = torch.empty_like(ids), torch.empty_like(lens)
+                slot["h_ids"] = torch.empty(ids.shape, dtype=ids.dtype).pin_memory()
+                slot["h_lens"] = torch.empty(lens.shape, dtype=lens.dtype).pin_memory()
+            slot["ids"].copy_(ids); slot["lens"].copy_(lens)     # the decode graph's static outputs are reused by the next batch
+            if after_decode is not None:
+                after_decode(slot["ids"], slot["lens"])        # e.g. the NCCL id gather, enqueued on the decode stream
+            if to_host:
+                slot["h_ids"].copy_(slot["ids"], non_blocking=True)
+                slot["h_lens"].copy_(slot["lens"], non_blocking=True)
+            slot["done"] = self.dec_stream.record_event()
+        self._n += 1
+        return ticket
+
+    def result(self, ticket: int, host: bool = True):
+        if ticket < self._n - self.DEPTH or ticket >= self._n:
+            raise L.VcError(f"ticket {ticket} is no longer (or not yet) in flight")
+        slot = self._slots[ticket % self.DEPTH]
+        slot["done"].synchronize()
+        return (slot["h_ids"], slot["h_lens"]) if host else (slot["ids"], slot["lens"])
+
+    def last_event(self):
+        return self._slots[(self._n - 1) % self.DEPTH]["done"] if self._n else None
+
+    def drain(self) -> None:
+        for s in (self.copy_stream, self.enc_stream, self.dec_stream):
+            s.synchronize()
