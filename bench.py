@@ -309,11 +309,16 @@ def run_b200(args):
         g_calls = sum(v["calls"] for k, v in kern.items() if k.startswith("gemm_"))
         achieved = g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
         enc_tflops = B * T * VIT_GFLOP_PER_FRAME / 1e3 / (enc_ms / 1e3)
+        traffic = None
+        tp = ROOT / "profiles" / "r1_gemm_traffic.json"
+        if tp.exists():
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch_avg")   # from the committed ncu pass, not measured live
         roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all epilogues, one ViT encoder pass)",
                     "achieved": round(achieved, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                     "frac": round(achieved / pk["tf_sustained"], 4), "peak_source": pk["source"] + " sustained bf16 (kernel timed inside a long step)",
                     "frac_of_burst": round(achieved / pk["tf_burst"], 4), "launches": g_calls, "avg_launch_ms": round(g_ms / max(g_calls, 1), 4),
-                    "flop_per_launch_avg": g_fl / max(g_calls, 1), "traffic": None,
+                    "flop_per_launch_avg": g_fl / max(g_calls, 1), "traffic": traffic,
+                    "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r1_gemm_traffic.json (launch mix of the first 4 layers)",
                     "encoder_stage_tflops": round(enc_tflops, 1), "encoder_stage_frac": round(enc_tflops / pk["tf_sustained"], 4)}
         decode = {"bound": "hbm", "step_p50_us": round(step_p50, 1), "bytes_per_step": int(step_bytes),
                   "achieved": round(step_bytes / (step_p50 * 1e-6) / 1e9, 1), "peak": pk["hbm"], "unit": "GB/s",

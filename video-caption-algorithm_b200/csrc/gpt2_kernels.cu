@@ -371,7 +371,7 @@ int greedy_init(int32_t* ids_out, int32_t* len_out, int32_t* finished, int n_seq
 
 // benchmark_baseline.py:210-227: next = argmax(logits[:, -1]); finished rows -> eos; unfinished rows
 // append the token (including their first eos) and become finished on eos; next input = wte(next).
-__global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restrict__ logits, long long ld, int vocab, int step, int max_new,
+__global__ void __launch_bounds__(1024) greedy_select_kernel(const float* __restrict__ logits, long long ld, int vocab, int step, int max_new,
                                                              int eos, int32_t* __restrict__ finished, int32_t* __restrict__ ids_out,
                                                              int32_t* __restrict__ len_out, const int32_t* __restrict__ forced,
                                                              const __nv_bfloat16* __restrict__ wte, int dim, float* __restrict__ next_embeds,
@@ -400,7 +400,7 @@ int greedy_select(const float* logits, long long ld, int vocab, int n_seq, int s
                   int32_t* next_ids, cudaStream_t s) {
   if (n_seq <= 0) return 0;
   VC_LAUNCH("greedy_select", static_cast<double>(n_seq) * vocab * 4.0, s,
-            VC_CUDA_OK(launch_pdl(greedy_select_kernel, dim3(n_seq), dim3(256), 0, s, logits, ld, vocab, step, max_new, eos, finished, ids_out, len_out,
+            VC_CUDA_OK(launch_pdl(greedy_select_kernel, dim3(n_seq), dim3(1024), 0, s, logits, ld, vocab, step, max_new, eos, finished, ids_out, len_out,
                                   forced, static_cast<const __nv_bfloat16*>(wte), dim, next_embeds, next_ids)));
   VC_CUDA_OK(cudaGetLastError());
   return 0;
