@@ -113,6 +113,9 @@ int vc_layernorm_f32_bf16(const float* x, const float* gamma, const float* beta,
                           float eps, vc_stream_t stream);
 int vc_vit_attention(const void* qkv_bf16, void* out_bf16, int n_frames, int tokens, int heads, int head_dim,
                      vc_stream_t stream);
+/* the mma.sync kernel vc_vit_attention falls back to for tokens > 256 (ViT-L/14: 257); exported for A/B tests */
+int vc_vit_attention_mma_sync(const void* qkv_bf16, void* out_bf16, int n_frames, int tokens, int heads, int head_dim,
+                              vc_stream_t stream);
 size_t vc_vit_workspace_bytes(const VcVitWeights* w, int chunk_frames);
 /* patches: bf16 [n_frames*(tokens-1), patch_k]; cls_out: fp32 [n_frames, dim] = final-LN class token per frame */
 int vc_vit_encode(const VcVitWeights* w, const void* patches_bf16, int n_frames, int chunk_frames, void* workspace,

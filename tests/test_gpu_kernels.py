@@ -175,6 +175,28 @@ def test_vit_attention(lib, frames, tokens, heads):
     assert (out.float() - ref).abs().max().item() < 0.03       # P rounded to bf16 before PV + bf16 output
 
 
+def test_vit_attention_tcgen05_agrees_with_mma_sync_kernel(lib):
+    """The tcgen05 kernel (S/P/O in TMEM) and the mma.sync kernel it replaced for tokens <= 256 compute the same
+    softmax(QK^T/8)V: both round P to bf16 before PV, so they agree to bf16 output rounding."""
+    frames, tokens, heads = 5, 197, 12
+    D = heads * 64
+    torch.manual_seed(3)
+    qkv = (torch.randn(frames * tokens, 3 * D, device=DEV) * 1.5).to(torch.bfloat16)
+    a = torch.zeros(frames * tokens, D, device=DEV, dtype=torch.bfloat16)
+    b = torch.zeros_like(a)
+    L.check(lib.vc_vit_attention(qkv.data_ptr(), a.data_ptr(), frames, tokens, heads, 64, _stream()))
+    L.check(lib.vc_vit_attention_mma_sync(qkv.data_ptr(), b.data_ptr(), frames, tokens, heads, 64, _stream()))
+    torch.cuda.synchronize()
+    assert (a.float() - b.float()).abs().max().item() < 0.02
+    # frames are independent: the result of frame 2 does not depend on what surrounds it (the kernel's K/V tiles run
+    # over the frame boundary and rely on masking)
+    c = torch.zeros(tokens, D, device=DEV, dtype=torch.bfloat16)
+    one = qkv[2 * tokens:3 * tokens].contiguous()
+    L.check(lib.vc_vit_attention(one.data_ptr(), c.data_ptr(), 1, tokens, heads, 64, _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(c, a[2 * tokens:3 * tokens])
+
+
 # ------------------------------------------------------------------ pool / prefix and the two CuPy-hook operators
 def test_pool_prefix_matches_oracle(lib):
     B, T, D, Vd, Pn, H = 3, 4, 768, 256, 4, 768

@@ -8,7 +8,10 @@ import numpy as np
 import pytest
 import torch
 
+from pathlib import Path
+
 import vcb200  # noqa: F401
+from vcb200 import lib as L
 from vcb200 import synthetic
 from vcb200.model import B200CaptionModel
 from vcb200.memory import KvCache
@@ -16,6 +19,7 @@ from oracle import vc_oracle as O
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+ROOT = Path(__file__).resolve().parents[1]
 
 FEAT_MAXABS, FEAT_COS = 0.02, 0.9999          # north_star: bf16 encoder features within stated tolerance
 LOGIT_MAXABS, LOGIT_COS = 0.06, 0.9995        # teacher-forced logits
@@ -283,3 +287,63 @@ def test_engine_three_candidates_encode_once():
     assert m2 > 0
     with pytest.raises(ValueError):
         InferenceEngine(InferenceConfig(device=DEV, backend="tensorrt"), state_dict=sd)
+
+
+def test_pipeline_equals_sequential_captions():
+    """CaptionPipeline (H2D / encode / decode of consecutive batches on three streams) returns, for every batch, exactly
+    the ids of the plain sequential call — device-resident and pinned-host inputs, more batches than pipeline slots."""
+    a, sd, m = _model("tiny")
+    batches = [synthetic.make_batch_u8(10 * i, 3, 2) for i in range(5)]
+    want = []
+    for f in batches:
+        ids, lens = m.caption_ids(f.to(DEV), max_new_tokens=6)
+        torch.cuda.synchronize()
+        want.append((ids.cpu().clone(), lens.cpu().clone()))
+    pipe = m.pipeline(max_new_tokens=6)
+    tickets = []
+    got = {}
+    for i, f in enumerate(batches):
+        src = f.pin_memory() if i % 2 else f.to(DEV)
+        tickets.append(pipe.submit(src))
+        if i >= 2:                                   # collect with a lag, like a serving loop would
+            t = tickets[i - 2]
+            ids, lens = pipe.result(t)
+            got[t] = (ids.clone(), lens.clone())
+    for t in tickets[-2:]:
+        ids, lens = pipe.result(t)
+        got[t] = (ids.clone(), lens.clone())
+    pipe.drain()
+    for t, (wi, wl) in zip(tickets, want):
+        assert torch.equal(got[t][0], wi) and torch.equal(got[t][1], wl)
+    with pytest.raises(L.VcError):
+        pipe.result(tickets[0])                      # its slot has been reused
+
+
+def test_persistent_decode_kernel_matches_kernel_chain():
+    """VC_DECODE_PERSISTENT=1 (one cooperative launch for all decode steps: decode_step.cu) must produce the same
+    teacher-forced logits, to fp32 summation-order noise, and the same ids as the default PDL kernel chain."""
+    import os, subprocess, sys, tempfile
+    code = (
+        "import sys, torch; sys.path.insert(0, %r); import vcb200; from vcb200 import synthetic; from vcb200.model import B200CaptionModel\n"
+        "a = synthetic.ARCHS['tiny']; sd = synthetic.make_state_dict(a, seed=1234)\n"
+        "m = B200CaptionModel(sd, 'cuda:0', vit_heads=a.vit_heads, gpt_heads=a.gpt_heads)\n"
+        "g = torch.Generator().manual_seed(11); prefix = (torch.randn(5, a.prefix_len, a.gpt_dim, generator=g) * 0.3).cuda()\n"
+        "forced = torch.randint(0, 50000, (5, 7), generator=g).int().cuda()\n"
+        "ids, lens, lg = m.greedy_ids(prefix, None, 7, forced_ids=forced, keep_logits=True)\n"
+        "ids2, lens2, _ = m.greedy_ids(prefix, None, 7)\n"
+        "torch.cuda.synchronize(); torch.save(dict(lg=lg.cpu(), ids=ids.cpu().clone(), ids2=ids2.cpu().clone(), lens2=lens2.cpu().clone()), sys.argv[1])\n"
+    ) % str(ROOT)
+    outs = []
+    with tempfile.TemporaryDirectory() as td:
+        for flag in ("0", "1"):
+            path = os.path.join(td, f"o{flag}.pt")
+            env = dict(os.environ, VC_DECODE_PERSISTENT=flag)
+            r = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs.append(torch.load(path))
+    a_, b_ = outs
+    assert (a_["lg"] - b_["lg"]).abs().max().item() < 2e-2
+    assert _cos_min(a_["lg"].flatten(0, 1), b_["lg"].flatten(0, 1)) > 0.9999
+    assert torch.equal(a_["ids"], b_["ids"])         # teacher-forced bookkeeping is identical
+    agree = (a_["ids2"] == b_["ids2"]).float().mean().item()
+    assert agree >= 0.9                               # free-running: only a near-tie may flip a token

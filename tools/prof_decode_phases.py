@@ -2,6 +2,7 @@
 phase complete.  Prints the mean duration of each phase kind over the steps of one greedy run."""
 import os, sys
 os.environ["VC_DK_PROF"] = "1"
+os.environ["VC_DECODE_PERSISTENT"] = "1"
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import torch

@@ -186,6 +186,10 @@ int vc_vit_attention(const void* qkv_bf16, void* out_bf16, int n_frames, int tok
   return vit_attention(qkv_bf16, out_bf16, n_frames, tokens, heads, head_dim, S(stream));
 }
 
+int vc_vit_attention_mma_sync(const void* qkv_bf16, void* out_bf16, int n_frames, int tokens, int heads, int head_dim, vc_stream_t stream) {
+  return vit_attention_mma_sync(qkv_bf16, out_bf16, n_frames, tokens, heads, head_dim, S(stream));
+}
+
 size_t vc_vit_workspace_bytes(const VcVitWeights* w, int chunk_frames) { return carve_vit(w, chunk_frames, nullptr).total; }
 
 int vc_vit_encode(const VcVitWeights* w, const void* patches_bf16, int n_frames, int chunk_frames, void* workspace,

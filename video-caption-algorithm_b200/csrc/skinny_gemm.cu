@@ -34,9 +34,18 @@ constexpr int SK_BN = SK_WARPS * 16;
 constexpr int SK_MT = 64;               // sequences per CTA pass (8 n-tiles of 8)
 constexpr int SK_KB = 64;               // k elements per register batch (2 MMA pairs)
 
-__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+// Weights are streamed once per step: keep them out of L1 and mark them first-to-evict in L2, so that 247 MB of decoder
+// weights per step do not push the concurrently running encoder's working set out of the 126 MB L2 (CaptionPipeline).
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint4 ldg_stream(const void* p, uint64_t pol) {
   uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(pol));
   return r;
 }
 __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
@@ -73,10 +82,11 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const __nv_b
   const int nb = kslice / SK_KB;
   // two register buffers with compile-time names (A/B) so nothing lands in local memory
   uint4 wA[4], wB[4];   // {lo step0, hi step0, lo step1, hi step1}
+  const uint64_t pol = l2_evict_first_policy();
   auto load = [&](uint4 (&w)[4], int b) {
     const int o = b * SK_KB;
-    w[0] = ldg_stream(w_lo + o);      w[1] = ldg_stream(w_hi + o);
-    w[2] = ldg_stream(w_lo + o + 32); w[3] = ldg_stream(w_hi + o + 32);
+    w[0] = ldg_stream(w_lo + o, pol);      w[1] = ldg_stream(w_hi + o, pol);
+    w[2] = ldg_stream(w_lo + o + 32, pol); w[3] = ldg_stream(w_hi + o + 32, pol);
   };
   auto compute = [&](const uint4 (&w)[4], int b) {
 #pragma unroll

@@ -49,6 +49,7 @@ int layernorm_rows(const float* x, long long row_stride, long long row_offset, c
 int add_layernorm_rows(float* x, const void* delta_bf16, long long row_stride, long long row_offset, const float* g, const float* b,
                        float* out_f32, void* out_bf16, int rows, int dim, float eps, cudaStream_t s);
 int vit_attention(const void* qkv, void* out, int n_frames, int tokens, int heads, int head_dim, cudaStream_t s);
+int vit_attention_mma_sync(const void* qkv, void* out, int n_frames, int tokens, int heads, int head_dim, cudaStream_t s);
 // vit_attention_tc.cu: tcgen05 / TMEM version (tokens <= 256, head_dim 64); vit_attention() dispatches to it
 bool vit_attention_tc_supported(int tokens, int heads, int head_dim);
 int vit_attention_tc(const void* qkv, void* out, int n_frames, int tokens, int heads, cudaStream_t s);

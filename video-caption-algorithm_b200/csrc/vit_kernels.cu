@@ -423,6 +423,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) vit_attention_kernel(const __n
   }
 }
 
+int vit_attention_mma_sync(const void* qkv, void* out, int n_frames, int tokens, int heads, int head_dim, cudaStream_t s);
+
 int vit_attention(const void* qkv, void* out, int n_frames, int tokens, int heads, int head_dim, cudaStream_t s) {
   VC_REQUIRE(head_dim == HD, "vit_attention: head_dim=%d (only 64 is built)", head_dim);
   VC_REQUIRE(tokens > 0 && tokens <= 576, "vit_attention: tokens=%d out of range", tokens);
@@ -431,6 +433,13 @@ int vit_attention(const void* qkv, void* out, int n_frames, int tokens, int head
   static const bool legacy = getenv("VC_VIT_ATTENTION_MMA_SYNC") != nullptr;
   if (!legacy && vit_attention_tc_supported(tokens, heads, head_dim) && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0)
     return vit_attention_tc(qkv, out, n_frames, tokens, heads, s);
+  return vit_attention_mma_sync(qkv, out, n_frames, tokens, heads, head_dim, s);
+}
+
+int vit_attention_mma_sync(const void* qkv, void* out, int n_frames, int tokens, int heads, int head_dim, cudaStream_t s) {
+  VC_REQUIRE(head_dim == HD, "vit_attention: head_dim=%d (only 64 is built)", head_dim);
+  VC_REQUIRE(tokens > 0 && tokens <= 576, "vit_attention: tokens=%d out of range", tokens);
+  if (n_frames <= 0) return 0;
   const int s_pad = ((tokens + 63) / 64) * 64;
   const int smem = 3 * s_pad * 128;
   static int attr_smem = 0;

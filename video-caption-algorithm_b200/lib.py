@@ -98,6 +98,7 @@ _SIGNATURES = {
     "vc_gemm_bf16": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p]),
     "vc_layernorm_f32_bf16": (_i, [_p, _p, _p, _p, _i, _i, _f, _p]),
     "vc_vit_attention": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "vc_vit_attention_mma_sync": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "vc_vit_workspace_bytes": (_sz, [C.POINTER(VcVitWeights), _i]),
     "vc_vit_encode": (_i, [C.POINTER(VcVitWeights), _p, _i, _i, _p, _sz, _p, _p]),
     "vc_pool_prefix": (_i, [_p, _i, _i, _i, _p, _p, _i, _f, _f, _p, _p, _i, _p, _p, _p]),
