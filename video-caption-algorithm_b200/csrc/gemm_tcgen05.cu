@@ -10,7 +10,7 @@
 //   * one elected thread of the leader CTA issues tcgen05.mma (M=256, N=256, K=16); fp32
 //     accumulators live in TMEM (128 lanes x 256 columns per CTA), double-buffered so the epilogue
 //     of tile i overlaps the MMAs of tile i+1;
-//   * 8 epilogue warps per CTA read TMEM with tcgen05.ld (one accumulator row per thread),
+//   * 12 epilogue warps per CTA read TMEM with tcgen05.ld (one accumulator row per thread),
 //     transpose 32x32 blocks through swizzled shared memory and then apply bias / GELU /
 //     residual-add / patch-embed scatter with fully coalesced global accesses.
 //
@@ -43,7 +43,7 @@ constexpr int A_BYTES = BM * BK * 2;          // 16 KB
 constexpr int B_BYTES = (BN / 2) * BK * 2;    // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int TMEM_COLS = 512;         // 2 accumulators x 256 fp32 columns
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 12;            // 3 per TMEM lane quarter: column chunks (of 32) 0-2, 3-5, 6-7 of the 256-wide tile
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // one 32x32 fp32 block per warp
 constexpr int THREADS = (2 + EPI_WARPS) * 32;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -220,7 +220,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     // ------------------------------------------------ epilogue warps (both CTAs)
     const int ew = warp - 2;            // 0..7
     const int quarter = warp & 3;       // TMEM lane quarter this warp may read
-    const int half = ew >> 2;           // which 128 columns of the 256-wide tile
+    const int part = ew >> 2;           // which column chunks of the 256-wide tile: 0 -> 0..2, 1 -> 3..5, 2 -> 6..7
+    const int c_begin = part * 3, c_end = part == 2 ? 8 : part * 3 + 3;
     uint8_t* stg = epi_stage + ew * EPI_STAGE_BYTES;
     const uint32_t tempty_leader0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     const uint32_t tempty_leader1 = mapa_shared(smem_u32(&tempty_bar[1]), 0);
@@ -232,8 +233,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       tc_fence_after();
       const int row_base = m0 + quarter * 32;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int col_in_tile = half * 128 + c * 32;
+      for (int c = c_begin; c < c_end; ++c) {
+        const int col_in_tile = c * 32;
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_in_tile, r);
         tmem_ld_wait();
