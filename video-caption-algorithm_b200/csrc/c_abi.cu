@@ -58,7 +58,7 @@ static inline cudaStream_t S(vc_stream_t s) { return reinterpret_cast<cudaStream
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct VitBuffers {
-  float* x; void* xn; void* qkv; void* att; void* hid; void* delta; size_t total;
+  float* x; void* xn; void* qkv; void* att; void* hid; void* delta; void* delta2; size_t total;
 };
 static VitBuffers carve_vit(const VcVitWeights* w, int chunk_frames, void* base) {
   const size_t M = static_cast<size_t>(chunk_frames) * w->tokens;
@@ -71,6 +71,7 @@ static VitBuffers carve_vit(const VcVitWeights* w, int chunk_frames, void* base)
   b.att = p + off;                          off += align_up(M * w->dim * 2, 1024);
   b.hid = p + off;                          off += align_up(M * w->mlp * 2, 1024);
   b.delta = p + off;                        off += align_up(M * w->dim * 2, 1024);
+  b.delta2 = p + off;                       off += align_up(M * w->dim * 2, 1024);
   b.total = off;
   return b;
 }
@@ -211,22 +212,26 @@ int vc_vit_encode(const VcVitWeights* w, const void* patches_bf16, int n_frames,
     // tokens: [cls + pos0 | conv_proj(patches) + bias + pos]   (video_encoder.py:90-95, Encoder.forward)
     if ((e = cls_rows_init(b.x, w->cls_pos0, nf, N, D, s))) return e;
     if ((e = gemm_bf16(patches, w->patch_w, w->patch_b, nf * P, D, w->patch_k, VC_EPI_PATCH_EMBED, b.x, D, w->pos, P, 0, s))) return e;
-    // The bias-added outputs of proj / fc2 go to `delta` in bf16 (write-only epilogue); the following LayerNorm
-    // kernel folds them into the fp32 residual stream before normalising.
-    const void* pending = nullptr;
+    // The bias-added outputs of proj / fc2 go to `delta` / `delta2` in bf16 (write-only epilogues); the LayerNorm kernels
+    // fold them into the fp32 residual stream, which is stored once per block (by the next block's LN1).
+    bool pending = false;
     for (int l = 0; l < w->layers; ++l) {
       const VcVitLayer& L = w->layer[l];
-      if ((e = add_layernorm_rows(b.x, pending, 1, 0, L.ln1_g, L.ln1_b, nullptr, b.xn, M, D, 1e-6f, s))) return e;
+      if ((e = add_layernorm_rows(b.x, pending ? b.delta : nullptr, pending ? b.delta2 : nullptr, 1, 1, 0, L.ln1_g, L.ln1_b, nullptr, b.xn, M, D,
+                                  1e-6f, s)))
+        return e;
       if ((e = gemm_bf16(b.xn, L.qkv_w, L.qkv_b, M, 3 * D, D, VC_EPI_BIAS, b.qkv, 3 * D, nullptr, 0, 0, s))) return e;
       if ((e = vit_attention(b.qkv, b.att, nf, N, w->heads, 64, s))) return e;
       if ((e = gemm_bf16(b.att, L.proj_w, L.proj_b, M, D, D, VC_EPI_BIAS, b.delta, D, nullptr, 0, 0, s))) return e;
-      if ((e = add_layernorm_rows(b.x, b.delta, 1, 0, L.ln2_g, L.ln2_b, nullptr, b.xn, M, D, 1e-6f, s))) return e;
+      if ((e = add_layernorm_rows(b.x, b.delta, nullptr, 0, 1, 0, L.ln2_g, L.ln2_b, nullptr, b.xn, M, D, 1e-6f, s))) return e;
       if ((e = gemm_bf16(b.xn, L.fc1_w, L.fc1_b, M, w->mlp, D, gelu, b.hid, w->mlp, nullptr, 0, 0, s))) return e;
-      if ((e = gemm_bf16(b.hid, L.fc2_w, L.fc2_b, M, D, w->mlp, VC_EPI_BIAS, b.delta, D, nullptr, 0, 0, s))) return e;
-      pending = b.delta;
+      if ((e = gemm_bf16(b.hid, L.fc2_w, L.fc2_b, M, D, w->mlp, VC_EPI_BIAS, b.delta2, D, nullptr, 0, 0, s))) return e;
+      pending = true;
     }
     // only the class token of each frame is consumed downstream (video_encoder.py:256-258)
-    if ((e = add_layernorm_rows(b.x, pending, N, 0, w->lnf_g, w->lnf_b, cls_out + static_cast<size_t>(f0) * D, nullptr, nf, D, 1e-6f, s))) return e;
+    if ((e = add_layernorm_rows(b.x, pending ? b.delta : nullptr, pending ? b.delta2 : nullptr, 0, N, 0, w->lnf_g, w->lnf_b,
+                                cls_out + static_cast<size_t>(f0) * D, nullptr, nf, D, 1e-6f, s)))
+      return e;
   }
   return 0;
 }

@@ -129,7 +129,8 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, uint8_t* stg
 }
 
 template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+// 104 registers x 448 threads leave ~19K registers per SM: one CTA of the decode chain (skinny GEMM: 18.4K) fits beside this kernel
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(104)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles must sit on 1024-byte boundaries (same offsets in both CTAs of the pair)

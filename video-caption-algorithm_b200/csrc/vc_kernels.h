@@ -45,9 +45,9 @@ int layernorm_f32_bf16(const float* x, const float* g, const float* b, void* out
 // fp32 rows picked with a stride (class tokens / last positions): out = LN(x[r*row_stride + row_offset])
 int layernorm_rows(const float* x, long long row_stride, long long row_offset, const float* g, const float* b, float* out_f32,
                    void* out_bf16, int rows, int dim, float eps, cudaStream_t s);
-// x[r] += delta[r] (bf16, may be null) in place, then out = LN(x[r]) for r = i*row_stride + row_offset
-int add_layernorm_rows(float* x, const void* delta_bf16, long long row_stride, long long row_offset, const float* g, const float* b,
-                       float* out_f32, void* out_bf16, int rows, int dim, float eps, cudaStream_t s);
+// t = x[r] + delta[r] (+ delta2[r]) (bf16, may be null); out = LN(t); x[r] = t if write_x; r = i*row_stride + row_offset
+int add_layernorm_rows(float* x, const void* delta_bf16, const void* delta2_bf16, int write_x, long long row_stride, long long row_offset,
+                       const float* g, const float* b, float* out_f32, void* out_bf16, int rows, int dim, float eps, cudaStream_t s);
 int vit_attention(const void* qkv, void* out, int n_frames, int tokens, int heads, int head_dim, cudaStream_t s);
 int vit_attention_mma_sync(const void* qkv, void* out, int n_frames, int tokens, int heads, int head_dim, cudaStream_t s);
 // vit_attention_tc.cu: tcgen05 / TMEM version (tokens <= 256, head_dim 64); vit_attention() dispatches to it

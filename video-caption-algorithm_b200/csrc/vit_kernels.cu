@@ -151,14 +151,16 @@ int preprocess_u8(const uint8_t* frames, const float* lut, void* out, int n, int
 // =========================================================================== (residual add +) LayerNorm
 // One warp per row, fp32 residual stream, two-pass statistics in registers, bf16 and/or fp32 out.
 // With `delta` (bf16 [rows_total, dim], the bias-added output of the preceding proj / fc2 GEMM) the kernel first
-// folds it into the residual stream: x += delta (written back in fp32), then normalises.  That is the
+// folds it into the residual stream: x += delta, then normalises.  The residual is written back only once per
+// transformer block: LN2 normalises x + d_proj without storing it, the next block's LN1 stores x + d_proj + d_fc2.  That is the
 // reference's `x = x + attn(...)` / `x + mlp(...)` (torchvision EncoderBlock.forward, timm Block.forward;
 // src/models/video_encoder.py:168-171) with the Linear output in bf16 exactly as under autocast, and it keeps
 // the GEMM epilogue write-only: a read-modify-write of the fp32 stream inside the epilogue made the
 // N=768,K=768 projection latency-bound (250-420 TFLOP/s).
 constexpr int LN_MAX_V4 = 8;   // dim <= 1024
 
-__global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delta, long long row_stride,
+__global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delta,
+                                                        const __nv_bfloat16* __restrict__ delta2, int write_x, long long row_stride,
                                                         long long row_offset, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
                                                         int rows, int dim, float eps) {
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, c
   const long long in_row = static_cast<long long>(warp) * row_stride + row_offset;
   float4* src = reinterpret_cast<float4*>(x + in_row * dim);
   const uint2* dsrc = delta ? reinterpret_cast<const uint2*>(delta + in_row * dim) : nullptr;
+  const uint2* dsrc2 = delta2 ? reinterpret_cast<const uint2*>(delta2 + in_row * dim) : nullptr;
   const int nv = dim >> 7;   // float4 per lane
   float4 v[LN_MAX_V4];
   float sum = 0.f;
@@ -181,7 +184,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, c
         const uint2 d = dsrc[i * 32 + lane];
         const float2 a = unpack_bf16(d.x), b = unpack_bf16(d.y);
         v[i].x += a.x; v[i].y += a.y; v[i].z += b.x; v[i].w += b.y;
-        src[i * 32 + lane] = v[i];
+        if (dsrc2 != nullptr) {                      // (x + d1) + d2: the order the two residual adds happen in the model
+          const uint2 e = dsrc2[i * 32 + lane];
+          const float2 c = unpack_bf16(e.x), f = unpack_bf16(e.y);
+          v[i].x += c.x; v[i].y += c.y; v[i].z += f.x; v[i].w += f.y;
+        }
+        if (write_x) src[i * 32 + lane] = v[i];
       }
       sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
@@ -216,14 +224,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, c
     }
 }
 
-int add_layernorm_rows(float* x, const void* delta_bf16, long long row_stride, long long row_offset, const float* g, const float* b,
-                       float* out_f32, void* out_bf16, int rows, int dim, float eps, cudaStream_t s) {
+int add_layernorm_rows(float* x, const void* delta_bf16, const void* delta2_bf16, int write_x, long long row_stride, long long row_offset,
+                       const float* g, const float* b, float* out_f32, void* out_bf16, int rows, int dim, float eps, cudaStream_t s) {
+  VC_REQUIRE(delta2_bf16 == nullptr || delta_bf16 != nullptr, "layernorm: delta2 without delta");
   VC_REQUIRE(dim % 128 == 0 && dim <= 128 * LN_MAX_V4, "layernorm: dim=%d must be a multiple of 128 and <= %d", dim,
              128 * LN_MAX_V4);
   if (rows <= 0) return 0;
   const int grid = (rows + 7) / 8;
-  VC_LAUNCH(delta_bf16 ? "add_layernorm" : "layernorm", static_cast<double>(rows) * dim * (delta_bf16 ? 12.0 : 6.0), s,
-            (layernorm_kernel<<<grid, 256, 0, s>>>(x, static_cast<const __nv_bfloat16*>(delta_bf16), row_stride, row_offset, g, b, out_f32,
+  const double bytes_per_elem = 4.0 + (delta_bf16 ? 2.0 : 0.0) + (delta2_bf16 ? 2.0 : 0.0) + (delta_bf16 && write_x ? 4.0 : 0.0) + 2.0;
+  VC_LAUNCH(delta_bf16 ? "add_layernorm" : "layernorm", static_cast<double>(rows) * dim * bytes_per_elem, s,
+            (layernorm_kernel<<<grid, 256, 0, s>>>(x, static_cast<const __nv_bfloat16*>(delta_bf16), static_cast<const __nv_bfloat16*>(delta2_bf16),
+                                                   write_x, row_stride, row_offset, g, b, out_f32,
                                                    static_cast<__nv_bfloat16*>(out_bf16), rows, dim, eps)));
   VC_CUDA_OK(cudaGetLastError());
   return 0;
@@ -231,7 +242,7 @@ int add_layernorm_rows(float* x, const void* delta_bf16, long long row_stride, l
 
 int layernorm_rows(const float* x, long long row_stride, long long row_offset, const float* g, const float* b, float* out_f32,
                    void* out_bf16, int rows, int dim, float eps, cudaStream_t s) {
-  return add_layernorm_rows(const_cast<float*>(x), nullptr, row_stride, row_offset, g, b, out_f32, out_bf16, rows, dim, eps, s);
+  return add_layernorm_rows(const_cast<float*>(x), nullptr, nullptr, 0, row_stride, row_offset, g, b, out_f32, out_bf16, rows, dim, eps, s);
 }
 
 int layernorm_f32_bf16(const float* x, const float* g, const float* b, void* out, int rows, int dim, float eps, cudaStream_t s) {
