@@ -34,7 +34,10 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 ARCH = "vit_b16_gpt2"
-VIT_GFLOP_PER_FRAME = 35.126120448          # 2 x 17,563,060,224 MAC
+VIT_GFLOP_PER_FRAME_FULL = 35.126120448     # 2 x 17,563,060,224 MAC
+# last-block class-token pruning (declared): proj, MLP and attention of the last block run for 1 of 197 rows
+_PRUNED_MAC = (197 * 768 * 768 + 2 * 197 * 768 * 3072 + 2 * 197 * 197 * 768) * 196 / 197
+VIT_GFLOP_PER_FRAME = VIT_GFLOP_PER_FRAME_FULL - 2 * _PRUNED_MAC / 1e9   # executed work: 32.93 GFLOP per frame
 GPT_WEIGHT_BYTES = 247_306_752              # GPT-2 small bf16 weights + biases + LN
 KV_BYTES_PER_TOKEN = 36_864
 
@@ -319,7 +322,9 @@ def run_b200(args):
                     "frac_of_burst": round(achieved / pk["tf_burst"], 4), "launches": g_calls, "avg_launch_ms": round(g_ms / max(g_calls, 1), 4),
                     "flop_per_launch_avg": g_fl / max(g_calls, 1), "traffic": traffic,
                     "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r1_gemm_traffic.json (launch mix of the first 4 layers)",
-                    "encoder_stage_tflops": round(enc_tflops, 1), "encoder_stage_frac": round(enc_tflops / pk["tf_sustained"], 4)}
+                    "encoder_stage_tflops": round(enc_tflops, 1), "encoder_stage_frac": round(enc_tflops / pk["tf_sustained"], 4),
+                    "encoder_gflop_per_frame_executed": round(VIT_GFLOP_PER_FRAME, 3),
+                    "encoder_pruning": "last block: proj/MLP/attention for the class-token row only (-6.3 % of 35.126 GFLOP/frame)"}
         decode = {"bound": "hbm", "step_p50_us": round(step_p50, 1), "bytes_per_step": int(step_bytes),
                   "achieved": round(step_bytes / (step_p50 * 1e-6) / 1e9, 1), "peak": pk["hbm"], "unit": "GB/s",
                   "frac": round(step_bytes / (step_p50 * 1e-6) / 1e9 / pk["hbm"], 4), "n_seq": B, "S_range": [P0, P0 + n_new - 1],

@@ -53,6 +53,8 @@ int vit_attention_mma_sync(const void* qkv, void* out, int n_frames, int tokens,
 // vit_attention_tc.cu: tcgen05 / TMEM version (tokens <= 256, head_dim 64); vit_attention() dispatches to it
 bool vit_attention_tc_supported(int tokens, int heads, int head_dim);
 int vit_attention_tc(const void* qkv, void* out, int n_frames, int tokens, int heads, cudaStream_t s);
+// attention output of the class-token query only: out bf16 [n_frames, heads*64]
+int vit_cls_attention(const void* qkv, void* out, int n_frames, int tokens, int heads, int head_dim, cudaStream_t s);
 int cls_rows_init(float* x, const float* cls_pos0, int n_frames, int tokens, int dim, cudaStream_t s);
 int pool_prefix(const float* cls, int B, int T, int dim, const float* head_w, const float* head_b, int video_dim,
                 float ln_scale, float in_weight, const float* mapper_w, const float* mapper_b, int mapper_out,

@@ -466,6 +466,75 @@ int vit_attention_mma_sync(const void* qkv, void* out, int n_frames, int tokens,
   return 0;
 }
 
+// =========================================================================== class-token attention (last block)
+// Only the class token of the LAST block is consumed downstream (video_encoder.py:256-258), so in that block the
+// attention output is needed for one query per frame.  One warp per (frame, head): lanes split the keys for the
+// scores (one 128-byte K row per lane), then split head_dim for the weighted V sum (coalesced 128-byte rows).
+constexpr int CLS_MAX_TOKENS = 640;
+__global__ void __launch_bounds__(128) vit_cls_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                                                                int n_items, int tokens, int heads) {
+  __shared__ float s_p[4][CLS_MAX_TOKENS];
+  __shared__ float s_q[4][HD];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * 4 + warp;
+  if (item >= n_items) return;
+  const int frame = item / heads, head = item - frame * heads;
+  const int D = heads * HD;
+  const __nv_bfloat16* base = qkv + static_cast<long long>(frame) * tokens * 3 * D + head * HD;
+  {
+    const float2 q2 = unpack_bf16(*reinterpret_cast<const uint32_t*>(base + 2 * lane));   // query = row 0 (class token)
+    s_q[warp][2 * lane] = q2.x; s_q[warp][2 * lane + 1] = q2.y;
+  }
+  __syncwarp();
+  float mx = -INFINITY;
+  for (int j = lane; j < tokens; j += 32) {
+    const uint4* kp = reinterpret_cast<const uint4*>(base + static_cast<long long>(j) * 3 * D + D);
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = __ldg(kp + c);
+      const float4 qa = *reinterpret_cast<const float4*>(&s_q[warp][c * 8]), qb = *reinterpret_cast<const float4*>(&s_q[warp][c * 8 + 4]);
+      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      acc = fmaf(qa.x, a.x, acc); acc = fmaf(qa.y, a.y, acc); acc = fmaf(qa.z, b.x, acc); acc = fmaf(qa.w, b.y, acc);
+      acc = fmaf(qb.x, cc.x, acc); acc = fmaf(qb.y, cc.y, acc); acc = fmaf(qb.z, d.x, acc); acc = fmaf(qb.w, d.y, acc);
+    }
+    acc *= 0.125f;
+    s_p[warp][j] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < tokens; j += 32) {
+    const float e = __expf(s_p[warp][j] - mx);
+    s_p[warp][j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  float o0 = 0.f, o1 = 0.f;
+#pragma unroll 8
+  for (int j = 0; j < tokens; ++j) {
+    const float2 v = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(base + static_cast<long long>(j) * 3 * D + 2 * D) + lane));
+    const float pj = s_p[warp][j];
+    o0 = fmaf(pj, v.x, o0);
+    o1 = fmaf(pj, v.y, o1);
+  }
+  const float inv = 1.f / sum;
+  *(reinterpret_cast<uint32_t*>(out + static_cast<long long>(frame) * D + head * HD) + lane) = pack_bf16(o0 * inv, o1 * inv);
+}
+
+int vit_cls_attention(const void* qkv, void* out, int n_frames, int tokens, int heads, int head_dim, cudaStream_t s) {
+  VC_REQUIRE(head_dim == HD, "vit_cls_attention: head_dim=%d (only 64 is built)", head_dim);
+  VC_REQUIRE(tokens > 0 && tokens <= CLS_MAX_TOKENS, "vit_cls_attention: tokens=%d out of range", tokens);
+  if (n_frames <= 0) return 0;
+  const int items = n_frames * heads;
+  VC_LAUNCH("vit_cls_attention", 4.0 * items * static_cast<double>(tokens) * HD, s,
+            (vit_cls_attention_kernel<<<(items + 3) / 4, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), items,
+                                                                    tokens, heads)));
+  VC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // =========================================================================== pool + proj + prefix
 // One CTA per video: class-token temporal mean (video_encoder.py:256-258) -> encoder.proj
 // Linear(dim, video_dim) (:316) -> F.layer_norm(no affine) * ln_scale, * in_weight
