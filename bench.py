@@ -220,6 +220,7 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        pipe.drain()          # nothing left over from the warm-up joins (or is captured inside) the timed region
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -337,7 +338,8 @@ def run_b200(args):
                                    f"(BASELINE.json configs[1]; configs[2] layout at N>1), random-init weights",
                        "videos_per_gpu": B, "global_batch": world * B, "frames": T, "max_new_tokens": n_new,
                        "parallelism": f"videos sharded over {world} GPU(s), ids all_gather", "chunk_frames": args.chunk_frames,
-                       "pipelining": "batches back to back on 3 streams (H2D / encode / decode overlap across batches); stages_ms is one batch alone",
+                       "pipelining": "batches back to back on 3 streams (H2D / encode / decode overlap across batches, two encoder batches "
+                                     "per decode chain); stages_ms is one batch alone",
                        "l2": "inputs (154 MB uint8 frames) and per-layer activations (>300 MB) exceed the 126 MB L2 every step"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roofline, "decode": decode, "single_batch_ms": round(enc_ms + dec_ms, 3),

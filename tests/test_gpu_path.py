@@ -290,10 +290,11 @@ def test_engine_three_candidates_encode_once():
 
 
 def test_pipeline_equals_sequential_captions():
-    """CaptionPipeline (H2D / encode / decode of consecutive batches on three streams) returns, for every batch, exactly
-    the ids of the plain sequential call — device-resident and pinned-host inputs, more batches than pipeline slots."""
+    """CaptionPipeline (H2D / encode / decode of consecutive batches on three streams, two encoder batches per decode
+    chain) returns, for every batch, exactly the ids of the plain sequential call — device-resident and pinned-host inputs,
+    more batches than pipeline slots, an odd batch left over at the end."""
     a, sd, m = _model("tiny")
-    batches = [synthetic.make_batch_u8(10 * i, 3, 2) for i in range(5)]
+    batches = [synthetic.make_batch_u8(10 * i, 3, 2) for i in range(7)]
     want = []
     for f in batches:
         ids, lens = m.caption_ids(f.to(DEV), max_new_tokens=6)

@@ -289,9 +289,9 @@ class B200CaptionModel:
             torch.cuda.nvtx.range_pop()
         return ids, lengths
 
-    def pipeline(self, max_new_tokens: int = 20) -> "CaptionPipeline":
+    def pipeline(self, max_new_tokens: int = 20, decode_group: int = 2) -> "CaptionPipeline":
         """Throughput path: a three-stream software pipeline over batches (see CaptionPipeline)."""
-        return CaptionPipeline(self, max_new_tokens)
+        return CaptionPipeline(self, max_new_tokens, decode_group)
 
     def caption_from_host(self, frames_u8_host: torch.Tensor, max_new_tokens: int = 20, num_beams: int = 1):
         """End-to-end call with HOST buffers: pinned uint8 frames -> H2D -> pipeline -> ids D2H.
@@ -316,25 +316,30 @@ class CaptionPipeline:
         ids, lens = pipe.result(t0)    # host int32 tensors (pinned); blocks until that batch is done
     """
 
-    DEPTH = 3
-
-    def __init__(self, model: B200CaptionModel, max_new_tokens: int):
+    def __init__(self, model: B200CaptionModel, max_new_tokens: int, decode_group: int = 2):
+        """decode_group: consecutive batches whose sequences are decoded together (group * batch <= 128).  The decode
+        chain is latency-bound, not bandwidth-bound: 128 sequences cost about the same as 64, so decoding two encoder
+        batches per chain halves the decode cost per batch.  Per-sequence results do not depend on the grouping."""
         self.m = model
         self.max_new = int(max_new_tokens)
+        self.group = max(1, int(decode_group))
+        self.depth = 2 * self.group + 1
         dev = model.device
         with torch.cuda.device(dev):
             self.copy_stream = torch.cuda.Stream(dev)
             self.enc_stream = torch.cuda.Stream(dev)
             self.dec_stream = torch.cuda.Stream(dev, priority=-1)
-        self._slots = [dict(frames=None, ids=None, lens=None, done=None, enc_done=None, h_ids=None, h_lens=None) for _ in range(self.DEPTH)]
+        self._slots = [dict(frames=None, ids=None, lens=None, done=None, enc_done=None, h_ids=None, h_lens=None, prefix=None, cb=None, to_host=True)
+                       for _ in range(self.depth)]
+        self._pending: list = []       # tickets encoded but not yet decoded
         self._n = 0
+        self._last_done = None
 
     def submit(self, frames_u8: torch.Tensor, to_host: bool = True, after_decode=None) -> int:
         m, ticket = self.m, self._n
-        slot = self._slots[ticket % self.DEPTH]
+        slot = self._slots[ticket % self.depth]
         if slot["done"] is not None:
-            slot["done"].synchronize()                       # back-pressure: at most DEPTH batches in flight
-        B = frames_u8.shape[0]
+            slot["done"].synchronize()                       # back-pressure: at most `depth` batches in flight
         if frames_u8.device.type == "cpu":
             if slot["frames"] is None or slot["frames"].shape != frames_u8.shape:
                 slot["frames"] = torch.empty(frames_u8.shape, dtype=torch.uint8, device=m.device)
@@ -352,33 +357,61 @@ class CaptionPipeline:
             feat, prefix = m.encode_prefix(dev_frames)
             slot["enc_done"] = self.enc_stream.record_event()
             prefix.record_stream(self.dec_stream)
-        with torch.cuda.stream(self.dec_stream):
-            self.dec_stream.wait_event(slot["enc_done"])
-            ids, lens, _ = m.greedy_ids(prefix, None, self.max_new)
-            if slot["ids"] is None or slot["ids"].shape != ids.shape:
-                slot["ids"], slot["lens"] = torch.empty_like(ids), torch.empty_like(lens)
-                slot["h_ids"] = torch.empty(ids.shape, dtype=ids.dtype).pin_memory()
-                slot["h_lens"] = torch.empty(lens.shape, dtype=lens.dtype).pin_memory()
-            slot["ids"].copy_(ids); slot["lens"].copy_(lens)     # the decode graph's static outputs are reused by the next batch
-            if after_decode is not None:
-                after_decode(slot["ids"], slot["lens"])        # e.g. the NCCL id gather, enqueued on the decode stream
-            if to_host:
-                slot["h_ids"].copy_(slot["ids"], non_blocking=True)
-                slot["h_lens"].copy_(slot["lens"], non_blocking=True)
-            slot["done"] = self.dec_stream.record_event()
+        slot["prefix"], slot["cb"], slot["to_host"], slot["done"] = prefix, after_decode, to_host, None
+        self._pending.append(ticket)
         self._n += 1
+        if self._pending and (len(self._pending) >= self.group or
+                              sum(self._slots[t % self.depth]["prefix"].shape[0] for t in self._pending) * 2 > 128):
+            self._flush()
         return ticket
 
+    def _flush(self) -> None:
+        """Decode every encoded-but-undecoded batch as ONE chain."""
+        if not self._pending:
+            return
+        m = self.m
+        slots = [self._slots[t % self.depth] for t in self._pending]
+        self._pending = []
+        with torch.cuda.stream(self.dec_stream):
+            for sl in slots:
+                self.dec_stream.wait_event(sl["enc_done"])
+            prefix = slots[0]["prefix"] if len(slots) == 1 else torch.cat([sl["prefix"] for sl in slots], dim=0)
+            ids, lens, _ = m.greedy_ids(prefix, None, self.max_new)
+            o = 0
+            for sl in slots:
+                B = sl["prefix"].shape[0]
+                if sl["ids"] is None or sl["ids"].shape != (B, ids.shape[1]):
+                    sl["ids"] = torch.empty(B, ids.shape[1], dtype=ids.dtype, device=m.device)
+                    sl["lens"] = torch.empty(B, dtype=lens.dtype, device=m.device)
+                    sl["h_ids"] = torch.empty(sl["ids"].shape, dtype=ids.dtype).pin_memory()
+                    sl["h_lens"] = torch.empty(sl["lens"].shape, dtype=lens.dtype).pin_memory()
+                sl["ids"].copy_(ids[o:o + B]); sl["lens"].copy_(lens[o:o + B])   # the decode graph's static outputs are reused
+                o += B
+                if sl["cb"] is not None:
+                    sl["cb"](sl["ids"], sl["lens"])            # e.g. the NCCL id gather, enqueued on the decode stream
+                if sl["to_host"]:
+                    sl["h_ids"].copy_(sl["ids"], non_blocking=True)
+                    sl["h_lens"].copy_(sl["lens"], non_blocking=True)
+                sl["prefix"] = None
+            done = self.dec_stream.record_event()
+            for sl in slots:
+                sl["done"] = done
+            self._last_done = done
+
     def result(self, ticket: int, host: bool = True):
-        if ticket < self._n - self.DEPTH or ticket >= self._n:
+        if ticket < self._n - self.depth or ticket >= self._n:
             raise L.VcError(f"ticket {ticket} is no longer (or not yet) in flight")
-        slot = self._slots[ticket % self.DEPTH]
+        if ticket in self._pending:
+            self._flush()
+        slot = self._slots[ticket % self.depth]
         slot["done"].synchronize()
         return (slot["h_ids"], slot["h_lens"]) if host else (slot["ids"], slot["lens"])
 
     def last_event(self):
-        return self._slots[(self._n - 1) % self.DEPTH]["done"] if self._n else None
+        self._flush()
+        return self._last_done
 
     def drain(self) -> None:
+        self._flush()
         for s in (self.copy_stream, self.enc_stream, self.dec_stream):
             s.synchronize()
