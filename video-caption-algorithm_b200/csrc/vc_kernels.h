@@ -55,6 +55,8 @@ bool vit_attention_tc_supported(int tokens, int heads, int head_dim);
 int vit_attention_tc(const void* qkv, void* out, int n_frames, int tokens, int heads, cudaStream_t s);
 // attention output of the class-token query only: out bf16 [n_frames, heads*64]
 int vit_cls_attention(const void* qkv, void* out, int n_frames, int tokens, int heads, int head_dim, cudaStream_t s);
+// full attention of query rows row0..row0+n_rows-1 of every frame, written in place into out [n_frames*tokens, D]
+int vit_row_attention(const void* qkv, void* out, int n_frames, int tokens, int heads, int row0, int n_rows, cudaStream_t s);
 int cls_rows_init(float* x, const float* cls_pos0, int n_frames, int tokens, int dim, cudaStream_t s);
 int pool_prefix(const float* cls, int B, int T, int dim, const float* head_w, const float* head_b, int video_dim,
                 float ln_scale, float in_weight, const float* mapper_w, const float* mapper_b, int mapper_out,

@@ -11,6 +11,11 @@
 // NK/2 columns with P as packed bf16 pairs; O fp32 accumulates in [128, 192) (S is dead by then).  NK = tokens
 // rounded up to 16 (197 -> 208); keys >= tokens are masked to -inf, so their P is exactly 0.
 //
+// tokens in (256, 264] (ViT-L/14 has 257): the MMA covers keys 0..255 (N = 256 is the instruction's limit and the TMEM
+// budget of a tile); the few keys beyond are folded in on the CUDA cores of the softmax warps — score = q_row . k from the
+// Q tile in shared memory, and p * v added to the O row in the output pass — and the query rows beyond 255 are computed by
+// vit_row_attention (one warp per row).
+//
 // Softmax is fp32, exp2 with the 1/sqrt(64) * log2(e) scale folded in, row sum accumulated in fp32 before the bf16
 // rounding of P, output normalised at the end — the same arithmetic as the mma.sync kernel this replaces for
 // tokens <= 256 (reference: nn.MultiheadAttention / timm Attention -> SDPA, src/models/video_encoder.py:112-121).
@@ -28,6 +33,7 @@ int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* ptr, int rows, int K, int
 namespace {
 
 constexpr int AT_THREADS = 320;
+constexpr int AT_MAX_EXTRA = 8;              // keys / query rows beyond 256 handled outside the MMA
 constexpr int AT_Q_TILE = 128 * 128;            // bytes: 128 rows x 64 dims bf16
 constexpr int AT_KV_MAX = 256 * 128;            // bytes reserved for K (and V): up to 256 keys
 constexpr int AT_BUF = 2 * AT_Q_TILE + 2 * AT_KV_MAX;   // one item: Q0 Q1 K V = 96 KB
@@ -35,7 +41,8 @@ constexpr int AT_SMEM = 2 * AT_BUF + 1024 + 256;
 
 struct AttParams {
   __nv_bfloat16* out;
-  int n_frames, tokens, heads, D, NK, m_tiles;
+  const __nv_bfloat16* qkv;   // for the keys beyond the 256 the MMA covers (ViT-L/14: key 256)
+  int n_frames, tokens, heads, D, NK, m_tiles, extra;
 };
 
 __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -177,10 +184,40 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const uint32_t par = it & 1;
         const int frame = item / p.heads, head = item - frame * p.heads;
+        // keys beyond the MMA's 256: raw scores q_row . k_j on the CUDA cores, before waiting for the tensor core
+        float sx[AT_MAX_EXTRA];
+        if (p.extra > 0) {
+          const int buf = it & 1;
+          mbar_wait(&qkv_full[buf], (it >> 1) & 1);            // the Q tile of this item has landed
+          const uint8_t* qrow = smem + buf * AT_BUF + t * AT_Q_TILE + (quarter * 32 + lane) * 128;
+          const int rsw = (quarter * 32 + lane) & 7;
+          float q[64];
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            const uint4 u = *reinterpret_cast<const uint4*>(qrow + ((c8 ^ rsw) << 4));
+            const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+            q[c8 * 8 + 0] = a.x; q[c8 * 8 + 1] = a.y; q[c8 * 8 + 2] = b.x; q[c8 * 8 + 3] = b.y;
+            q[c8 * 8 + 4] = cc.x; q[c8 * 8 + 5] = cc.y; q[c8 * 8 + 6] = d.x; q[c8 * 8 + 7] = d.y;
+          }
+          for (int e = 0; e < p.extra; ++e) {
+            const uint4* kp = reinterpret_cast<const uint4*>(p.qkv + (static_cast<size_t>(frame) * p.tokens + NK + e) * 3 * p.D + p.D + head * 64);
+            float acc = 0.f;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+              const uint4 u = __ldg(kp + c8);
+              const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+              acc = fmaf(q[c8 * 8 + 0], a.x, acc); acc = fmaf(q[c8 * 8 + 1], a.y, acc); acc = fmaf(q[c8 * 8 + 2], b.x, acc);
+              acc = fmaf(q[c8 * 8 + 3], b.y, acc); acc = fmaf(q[c8 * 8 + 4], cc.x, acc); acc = fmaf(q[c8 * 8 + 5], cc.y, acc);
+              acc = fmaf(q[c8 * 8 + 6], d.x, acc); acc = fmaf(q[c8 * 8 + 7], d.y, acc);
+            }
+            sx[e] = acc;
+          }
+        }
         mbar_wait(&s_full[t], par);
         tc_fence_after();
         // pass 1: row max over the valid keys (64 columns per TMEM load: the loop is latency-, not bandwidth-bound)
         float mx = -INFINITY;
+        for (int e = 0; e < p.extra; ++e) mx = fmaxf(mx, sx[e]);
         int c = 0;
         for (; c + 64 <= NK; c += 64) {
           uint32_t r[64];
@@ -239,6 +276,10 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           }
           tmem_st_32x8(trow + (c >> 1), pk);
         }
+        for (int e = 0; e < p.extra; ++e) {
+          sx[e] = fast_ex2(fmaf(sx[e], scale, -m2));        // now the (unrounded) probability of the extra key
+          sum += sx[e];
+        }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -247,12 +288,28 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         mbar_wait(&o_full[t], par);
         tc_fence_after();
         const float inv = 1.f / sum;
-        const bool row_ok = row_in_frame < p.tokens;
+        const bool row_ok = row_in_frame < p.tokens;     // (tiles cover rows 0..255; rows beyond: vit_row_attention)
         __nv_bfloat16* orow = p.out + (static_cast<size_t>(frame) * p.tokens + row_in_frame) * p.D + head * 64;
         {
           uint32_t r[64];
           tmem_ld_32x64(trow + 128, r);
           tmem_ld_wait();
+          for (int e = 0; e < p.extra; ++e) {               // + p_j * v_j of the keys the MMA did not cover
+            const uint4* vp = reinterpret_cast<const uint4*>(p.qkv + (static_cast<size_t>(frame) * p.tokens + NK + e) * 3 * p.D + 2 * p.D + head * 64);
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+              const uint4 u = __ldg(vp + c8);
+              const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+              r[c8 * 8 + 0] = __float_as_uint(fmaf(sx[e], a.x, __uint_as_float(r[c8 * 8 + 0])));
+              r[c8 * 8 + 1] = __float_as_uint(fmaf(sx[e], a.y, __uint_as_float(r[c8 * 8 + 1])));
+              r[c8 * 8 + 2] = __float_as_uint(fmaf(sx[e], b.x, __uint_as_float(r[c8 * 8 + 2])));
+              r[c8 * 8 + 3] = __float_as_uint(fmaf(sx[e], b.y, __uint_as_float(r[c8 * 8 + 3])));
+              r[c8 * 8 + 4] = __float_as_uint(fmaf(sx[e], cc.x, __uint_as_float(r[c8 * 8 + 4])));
+              r[c8 * 8 + 5] = __float_as_uint(fmaf(sx[e], cc.y, __uint_as_float(r[c8 * 8 + 5])));
+              r[c8 * 8 + 6] = __float_as_uint(fmaf(sx[e], d.x, __uint_as_float(r[c8 * 8 + 6])));
+              r[c8 * 8 + 7] = __float_as_uint(fmaf(sx[e], d.y, __uint_as_float(r[c8 * 8 + 7])));
+            }
+          }
           if (row_ok) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -285,11 +342,14 @@ bool g_at_attr = false;
 
 }  // namespace
 
-bool vit_attention_tc_supported(int tokens, int heads, int head_dim) { return head_dim == 64 && tokens >= 1 && tokens <= 256 && heads >= 1; }
+bool vit_attention_tc_supported(int tokens, int heads, int head_dim) {
+  return head_dim == 64 && tokens >= 1 && tokens <= 256 + AT_MAX_EXTRA && heads >= 1;
+}
 
 int vit_attention_tc(const void* qkv, void* out, int n_frames, int tokens, int heads, cudaStream_t s) {
   const int D = heads * 64;
-  const int NK = (tokens + 15) / 16 * 16;
+  const int NK = tokens > 256 ? 256 : (tokens + 15) / 16 * 16;     // keys covered by the MMA
+  const int extra = tokens > 256 ? tokens - 256 : 0;               // keys and query rows handled outside it
   const int m_tiles = tokens > 128 ? 2 : 1;
   if (g_at_sms == 0) {
     int dev = 0;
@@ -305,7 +365,7 @@ int vit_attention_tc(const void* qkv, void* out, int n_frames, int tokens, int h
   int e;
   if ((e = make_tmap_bf16_kmajor(&tq, qkv, rows, 3 * D, 128))) return e;
   if ((e = make_tmap_bf16_kmajor(&tkv, qkv, rows, 3 * D, NK))) return e;
-  AttParams p{static_cast<__nv_bfloat16*>(out), n_frames, tokens, heads, D, NK, m_tiles};
+  AttParams p{static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(qkv), n_frames, tokens, heads, D, NK, m_tiles, extra};
   const int items = n_frames * heads;
   static const int sm_cap = getenv("VC_ENCODER_SMS") ? atoi(getenv("VC_ENCODER_SMS")) : 0;
   const int sms = sm_cap > 0 && sm_cap < g_at_sms ? sm_cap : g_at_sms;
@@ -315,6 +375,7 @@ int vit_attention_tc(const void* qkv, void* out, int n_frames, int tokens, int h
     vit_attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM, s>>>(tq, tkv, p);
   }
   VC_CUDA_OK(cudaGetLastError());
+  if (extra > 0) return vit_row_attention(qkv, out, n_frames, tokens, heads, 256, extra, s);   // query rows 256..tokens-1
   return 0;
 }
 

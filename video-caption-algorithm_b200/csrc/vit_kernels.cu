@@ -440,7 +440,7 @@ int vit_attention(const void* qkv, void* out, int n_frames, int tokens, int head
   VC_REQUIRE(head_dim == HD, "vit_attention: head_dim=%d (only 64 is built)", head_dim);
   VC_REQUIRE(tokens > 0 && tokens <= 576, "vit_attention: tokens=%d out of range", tokens);
   if (n_frames <= 0) return 0;
-  // tokens <= 256 (ViT-B/16: 197): the tcgen05 kernel; longer sequences (ViT-L/14: 257) stay on the mma.sync kernel below
+  // tokens <= 264 (ViT-B/16: 197, ViT-L/14: 257): the tcgen05 kernel; longer sequences stay on the mma.sync kernel below
   static const bool legacy = getenv("VC_VIT_ATTENTION_MMA_SYNC") != nullptr;
   if (!legacy && vit_attention_tc_supported(tokens, heads, head_dim) && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0)
     return vit_attention_tc(qkv, out, n_frames, tokens, heads, s);
@@ -471,18 +471,21 @@ int vit_attention_mma_sync(const void* qkv, void* out, int n_frames, int tokens,
 // attention output is needed for one query per frame.  One warp per (frame, head): lanes split the keys for the
 // scores (one 128-byte K row per lane), then split head_dim for the weighted V sum (coalesced 128-byte rows).
 constexpr int CLS_MAX_TOKENS = 640;
+// Generalised to any query row (row0 .. row0+n_rows-1 of every frame), with a compact ([n_frames*n_rows, D]) or an in-place
+// ([n_frames*tokens, D]) output: also used for the query rows the tcgen05 kernel leaves out when tokens > 256.
 __global__ void __launch_bounds__(128) vit_cls_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                                                                int n_items, int tokens, int heads) {
+                                                                int n_items, int tokens, int heads, int row0, int n_rows, int compact) {
   __shared__ float s_p[4][CLS_MAX_TOKENS];
   __shared__ float s_q[4][HD];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x * 4 + warp;
   if (item >= n_items) return;
-  const int frame = item / heads, head = item - frame * heads;
+  const int fr = item / heads, head = item - fr * heads;          // fr = frame * n_rows + row index
+  const int frame = fr / n_rows, qrow = row0 + (fr - frame * n_rows);
   const int D = heads * HD;
   const __nv_bfloat16* base = qkv + static_cast<long long>(frame) * tokens * 3 * D + head * HD;
   {
-    const float2 q2 = unpack_bf16(*reinterpret_cast<const uint32_t*>(base + 2 * lane));   // query = row 0 (class token)
+    const float2 q2 = unpack_bf16(*reinterpret_cast<const uint32_t*>(base + static_cast<long long>(qrow) * 3 * D + 2 * lane));
     s_q[warp][2 * lane] = q2.x; s_q[warp][2 * lane + 1] = q2.y;
   }
   __syncwarp();
@@ -520,7 +523,19 @@ __global__ void __launch_bounds__(128) vit_cls_attention_kernel(const __nv_bfloa
     o1 = fmaf(pj, v.y, o1);
   }
   const float inv = 1.f / sum;
-  *(reinterpret_cast<uint32_t*>(out + static_cast<long long>(frame) * D + head * HD) + lane) = pack_bf16(o0 * inv, o1 * inv);
+  const long long orow = compact ? fr : static_cast<long long>(frame) * tokens + qrow;
+  *(reinterpret_cast<uint32_t*>(out + orow * D + head * HD) + lane) = pack_bf16(o0 * inv, o1 * inv);
+}
+
+int vit_row_attention(const void* qkv, void* out, int n_frames, int tokens, int heads, int row0, int n_rows, cudaStream_t s) {
+  VC_REQUIRE(tokens > 0 && tokens <= CLS_MAX_TOKENS && row0 >= 0 && n_rows > 0 && row0 + n_rows <= tokens, "vit_row_attention: bad rows");
+  if (n_frames <= 0) return 0;
+  const int items = n_frames * n_rows * heads;
+  VC_LAUNCH("vit_row_attention", 4.0 * items * static_cast<double>(tokens) * HD, s,
+            (vit_cls_attention_kernel<<<(items + 3) / 4, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), items,
+                                                                    tokens, heads, row0, n_rows, 0)));
+  VC_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 int vit_cls_attention(const void* qkv, void* out, int n_frames, int tokens, int heads, int head_dim, cudaStream_t s) {
@@ -530,7 +545,7 @@ int vit_cls_attention(const void* qkv, void* out, int n_frames, int tokens, int 
   const int items = n_frames * heads;
   VC_LAUNCH("vit_cls_attention", 4.0 * items * static_cast<double>(tokens) * HD, s,
             (vit_cls_attention_kernel<<<(items + 3) / 4, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), items,
-                                                                    tokens, heads)));
+                                                                    tokens, heads, 0, 1, 1)));
   VC_CUDA_OK(cudaGetLastError());
   return 0;
 }
