@@ -320,9 +320,10 @@ def test_pipeline_equals_sequential_captions():
         pipe.result(tickets[0])                      # its slot has been reused
 
 
-def test_persistent_decode_kernel_matches_kernel_chain():
-    """VC_DECODE_PERSISTENT=1 (one cooperative launch for all decode steps: decode_step.cu) must produce the same
-    teacher-forced logits, to fp32 summation-order noise, and the same ids as the default PDL kernel chain."""
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_persistent_decode_kernel_matches_kernel_chain(mode):
+    """VC_DECODE_PERSISTENT=1 / 2 (one cooperative launch for all decode steps: decode_step.cu / decode_lean.cu) must
+    produce the same teacher-forced logits, to fp32 summation-order noise, and the same ids as the PDL kernel chain."""
     import os, subprocess, sys, tempfile
     code = (
         "import sys, torch; sys.path.insert(0, %r); import vcb200; from vcb200 import synthetic; from vcb200.model import B200CaptionModel\n"
@@ -336,7 +337,7 @@ def test_persistent_decode_kernel_matches_kernel_chain():
     ) % str(ROOT)
     outs = []
     with tempfile.TemporaryDirectory() as td:
-        for flag in ("0", "1"):
+        for flag in ("0", mode):
             path = os.path.join(td, f"o{flag}.pt")
             env = dict(os.environ, VC_DECODE_PERSISTENT=flag)
             r = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True, timeout=600)

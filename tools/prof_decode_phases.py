@@ -2,7 +2,7 @@
 phase complete.  Prints the mean duration of each phase kind over the steps of one greedy run."""
 import os, sys
 os.environ["VC_DK_PROF"] = "1"
-os.environ["VC_DECODE_PERSISTENT"] = "1"
+os.environ["VC_DECODE_PERSISTENT"] = sys.argv[3] if len(sys.argv) > 3 else "1"
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import torch
@@ -56,3 +56,16 @@ for k, v in acc.items():
     if v:
         print(f"{k:8s} mean {sum(v) / len(v):8.2f} us   min {min(v):8.2f}  max {max(v):8.2f}  n={len(v)}")
 
+if os.environ["VC_DECODE_PERSISTENT"] == "2":
+    c0, t0, c1, t1 = prof[2990:2994].tolist()
+    print(f"SM clock during the kernel: {(c1 - c0) / (t1 - t0) * 1e3:.0f} MHz over {(t1 - t0) / 1e3:.0f} us")
+    st = prof[3000:3000 + 800].tolist()
+    tags = {1: "arrive", 2: "released", 10: "gemm in", 11: "x staged", 12: "mma done", 13: "loads issued", 14: "cp.async done", 15: "warp mma", 16: "warp sts", 20: "ln in", 21: "ln summed", 22: "ln done",
+            30: "att in", 31: "att qkv", 32: "att scores", 33: "att pv"}
+    prev = None
+    for i in range(0, 800, 2):
+        tag, tm = st[i], st[i + 1]
+        if tag == 0 or tag not in tags:
+            break
+        print(f"  {str(tags.get(tag, tag)):14s} +{(tm - prev) / 1e3 if prev else 0:6.2f} us")
+        prev = tm

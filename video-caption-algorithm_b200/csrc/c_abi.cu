@@ -101,7 +101,7 @@ static GptBuffers carve_gpt(const VcGptWeights* w, int n_seq, int max_rows, void
     // fp32 split-K partials of the decode step's GEMMs (widest product), per-CTA argmax candidates, grid barrier
     const size_t rows = n_seq < kDecodeMaxRows ? n_seq : kDecodeMaxRows;
     const int H = w->dim;
-    size_t m = decode_partial_floats_per_row(w);
+    size_t m = std::max(decode_partial_floats_per_row(w), decode_lean_partial_floats_per_row(w));
     m = std::max(m, static_cast<size_t>(skinny_ksplit(3 * H, H)) * 3 * H);
     m = std::max(m, static_cast<size_t>(skinny_ksplit(H, H)) * H);
     m = std::max(m, static_cast<size_t>(skinny_ksplit(4 * H, H)) * 4 * H);
@@ -298,9 +298,14 @@ static int gpt_step_skinny(const VcGptWeights* w, const float* embeds, int n_seq
 
 // VC_DECODE_PERSISTENT=1 selects the single-launch cooperative decode kernel (decode_step.cu); measured on B200 it is
 // device-barrier bound (~86 barriers x ~4.5 us per step) and not yet faster than the PDL kernel chain, which is the default.
-static bool use_persistent_decode() {
-  static const bool on = getenv("VC_DECODE_PERSISTENT") != nullptr && getenv("VC_DECODE_PERSISTENT")[0] == '1';
-  return on;
+// VC_DECODE_PERSISTENT=2 selects the lean persistent kernel (decode_lean.cu: symmetric warps, mma.sync, n_seq <= 64).
+static int persistent_decode_mode() {
+  static const int mode = getenv("VC_DECODE_PERSISTENT") != nullptr ? atoi(getenv("VC_DECODE_PERSISTENT")) : 0;
+  return mode;
+}
+static bool use_persistent_decode() { return persistent_decode_mode() == 1; }
+static bool use_lean_decode(const VcGptWeights* w, int n_seq, const VcKvCache* cache) {
+  return persistent_decode_mode() == 2 && decode_lean_supported(w, n_seq, cache);
 }
 
 static DecodeBuffers decode_buffers(const GptBuffers& b) {
@@ -312,6 +317,8 @@ static int gpt_forward_impl(const VcGptWeights* w, const float* embeds, int n_se
   const int H = w->dim, M = n_seq * L;
   int e;
   // one new position per sequence
+  if (L == 1 && past_len >= 1 && use_lean_decode(w, n_seq, cache))
+    return decode_lean_steps(w, decode_buffers(b), b.logits, cache, n_seq, past_len, 1, embeds, nullptr, logits_out, 0, s);
   if (L == 1 && past_len >= 1 && use_persistent_decode() && decode_supported(w, n_seq, cache))
     return decode_steps(w, decode_buffers(b), cache, n_seq, past_len, 1, embeds, nullptr, logits_out, 0, s);
   if (L == 1 && n_seq <= kDecodeMaxRows && w->vocab_pad % 64 == 0) return gpt_step_skinny(w, embeds, n_seq, past_len, cache, b, logits_out, s);
@@ -368,6 +375,11 @@ int vc_greedy_decode(const VcGptWeights* w, const float* prefix, int n_seq, int 
     const int L = step == 0 ? L0 : 1;
     const int past = step == 0 ? 0 : L0 + step - 1;
     float* lg = step_logits ? step_logits + static_cast<size_t>(step) * n_seq * w->vocab_pad : b.logits;
+    if (step == 1 && max_new > 1 && use_lean_decode(w, n_seq, cache)) {
+      DecodeGreedy g{1, max_new, eos, b.finished, ids_out, len_out, forced_ids, b.next};
+      return decode_lean_steps(w, decode_buffers(b), b.logits, cache, n_seq, past, max_new - 1, b.emb, &g, step_logits ? lg : nullptr,
+                               static_cast<long long>(n_seq) * w->vocab_pad, s);
+    }
     if (step == 1 && fused) {
       // steps 1..max_new-1 (argmax, bookkeeping and token feedback included) in ONE persistent launch
       DecodeGreedy g{1, max_new, eos, b.finished, ids_out, len_out, forced_ids, b.next};

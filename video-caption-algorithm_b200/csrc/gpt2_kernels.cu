@@ -56,11 +56,21 @@ __device__ __forceinline__ uint4 fetch_qkv8(const __nv_bfloat16* __restrict__ qk
                                             const float* __restrict__ bias, size_t plane, size_t row, int ld, int col) {
   if (P == nullptr) return *reinterpret_cast<const uint4*>(qkv + row * ld + col);
   float4 a = __ldg(reinterpret_cast<const float4*>(bias + col)), b = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
-  for (int s = 0; s < ksplit; ++s) {
-    const float* p = P + s * plane + row * ld + col;
-    const float4 u = *reinterpret_cast<const float4*>(p), v = *reinterpret_cast<const float4*>(p + 4);
-    a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
-    b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
+  for (int s0 = 0; s0 < ksplit; s0 += 6) {               // fixed summation order; 12 loads in flight
+    float4 u[6], v[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      if (s0 + i < ksplit) {
+        const float* p = P + (s0 + i) * plane + row * ld + col;
+        u[i] = *reinterpret_cast<const float4*>(p);
+        v[i] = *reinterpret_cast<const float4*>(p + 4);
+      }
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      if (s0 + i < ksplit) {
+        a.x += u[i].x; a.y += u[i].y; a.z += u[i].z; a.w += u[i].w;
+        b.x += v[i].x; b.y += v[i].y; b.z += v[i].z; b.w += v[i].w;
+      }
   }
   return make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
 }
@@ -155,8 +165,6 @@ __global__ void __launch_bounds__(128) gpt_attention_smem_kernel(const __nv_bflo
                                                                  int n_seq, int rows_total, int heads, int s_max, int L, int past_len) {
   extern __shared__ __align__(16) uint8_t s_kv[];            // K rows then V rows, ATT_ROW_B bytes each
   __shared__ float s_p[4][ATT_SMEM_MAX_S];
-  pdl_wait();
-  pdl_launch_dependents();
   const int seq = blockIdx.x / heads, head = blockIdx.x - seq * heads;
   const int H = heads * GHD;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -169,9 +177,29 @@ __global__ void __launch_bounds__(128) gpt_attention_smem_kernel(const __nv_bflo
   uint8_t* sK = s_kv;
   uint8_t* sV = s_kv + n_total * ATT_ROW_B;
   float* sQ = reinterpret_cast<float*>(s_kv + 2 * n_total * ATT_ROW_B);   // [L][64] fp32 (bf16-rounded values)
-  for (int i = tid; i < n_total * 16 + L * 8; i += blockDim.x) {
-    if (i >= n_total * 16) {                                             // query rows
-      const int qi = i - n_total * 16, l = qi >> 3, chunk = qi & 7;
+  // cached rows (positions < past_len): asynchronous 16-byte copies, all in flight at once
+  auto stage_cached = [&]() {
+    for (int i = tid; i < past_len * 16; i += blockDim.x) {
+      const int j = i >> 4, which = (i >> 3) & 1, chunk = i & 7;
+      const int phys = slot != nullptr ? slot[static_cast<long long>(seq) * s_max + j] : seq;
+      const __nv_bfloat16* src = (which ? vbase : kbase) + (static_cast<long long>(phys) * heads + head) * s_max * GHD + static_cast<long long>(j) * GHD;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32((which ? sV : sK) + j * ATT_ROW_B + chunk * 16)),
+                   "l"(reinterpret_cast<const uint4*>(src) + chunk)
+                   : "memory");
+    }
+  };
+  // Without a slot table the cached rows were written by this layer's attention kernels of EARLIER forward calls, i.e.
+  // at least two kernels back in the stream: they are complete before this kernel can start (a programmatic dependent
+  // launch starts only after its predecessor has passed its own wait), so they are requested before the wait and arrive
+  // while the QKV product is still running.  With a slot table (beam search) the table itself may be one kernel old.
+  if (slot == nullptr) stage_cached();
+  pdl_wait();
+  pdl_launch_dependents();
+  if (slot != nullptr) stage_cached();
+  // the L new rows (appended to the cache) and the L query rows
+  for (int i = tid; i < L * 24; i += blockDim.x) {
+    if (i >= L * 16) {                                                   // query rows
+      const int qi = i - L * 16, l = qi >> 3, chunk = qi & 7;
       const uint4 u = fetch_qkv8(qkv, P, ksplit, bias, plane_p, static_cast<size_t>(seq) * L + l, 3 * H, head * GHD + chunk * 8);
       const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
       float4* dst = reinterpret_cast<float4*>(sQ + l * GHD + chunk * 8);
@@ -179,18 +207,12 @@ __global__ void __launch_bounds__(128) gpt_attention_smem_kernel(const __nv_bflo
       dst[1] = make_float4(cc.x, cc.y, d.x, d.y);
       continue;
     }
-    const int j = i >> 4, which = (i >> 3) & 1, chunk = i & 7;
-    uint4 v;
-    if (j < past_len) {
-      const int phys = slot != nullptr ? slot[static_cast<long long>(seq) * s_max + j] : seq;
-      const __nv_bfloat16* src = (which ? vbase : kbase) + (static_cast<long long>(phys) * heads + head) * s_max * GHD + static_cast<long long>(j) * GHD;
-      v = reinterpret_cast<const uint4*>(src)[chunk];
-    } else {
-      v = fetch_qkv8(qkv, P, ksplit, bias, plane_p, static_cast<size_t>(seq) * L + (j - past_len), 3 * H, (1 + which) * H + head * GHD + chunk * 8);
-      reinterpret_cast<uint4*>((which ? vbase : kbase) + own + static_cast<long long>(j) * GHD)[chunk] = v;   // append to the cache
-    }
+    const int l = i >> 4, which = (i >> 3) & 1, chunk = i & 7, j = past_len + l;
+    const uint4 v = fetch_qkv8(qkv, P, ksplit, bias, plane_p, static_cast<size_t>(seq) * L + l, 3 * H, (1 + which) * H + head * GHD + chunk * 8);
+    reinterpret_cast<uint4*>((which ? vbase : kbase) + own + static_cast<long long>(j) * GHD)[chunk] = v;   // append to the cache
     *reinterpret_cast<uint4*>((which ? sV : sK) + j * ATT_ROW_B + chunk * 16) = v;
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
   const float scale = 0.125f;
   for (int l = warp; l < L; l += 4) {
@@ -279,9 +301,36 @@ __device__ int block_argmax(const float* __restrict__ row, int vocab) {
   __shared__ int s_i[32];
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int j = threadIdx.x; j < vocab; j += blockDim.x) {
-    const float v = row[j];
-    if (v > best || (v == best && j < bi)) { best = v; bi = j; }
+  if ((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+    // 16-byte loads, 8 in flight per thread: a 50k-entry row costs two memory round trips instead of a dozen
+    const int n4 = vocab >> 2;
+    for (int j0 = threadIdx.x; j0 < n4; j0 += blockDim.x * 8) {
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = j0 + i * blockDim.x;
+        if (j < n4) v[i] = reinterpret_cast<const float4*>(row)[j];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = j0 + i * blockDim.x;
+        if (j < n4) {                                   // increasing index order, strict '>' keeps the lowest index of a tie
+          if (v[i].x > best) { best = v[i].x; bi = 4 * j; }
+          if (v[i].y > best) { best = v[i].y; bi = 4 * j + 1; }
+          if (v[i].z > best) { best = v[i].z; bi = 4 * j + 2; }
+          if (v[i].w > best) { best = v[i].w; bi = 4 * j + 3; }
+        }
+      }
+    }
+    for (int j = (n4 << 2) + threadIdx.x; j < vocab; j += blockDim.x) {
+      const float v = row[j];
+      if (v > best || (v == best && j < bi)) { best = v; bi = j; }
+    }
+  } else {
+    for (int j = threadIdx.x; j < vocab; j += blockDim.x) {
+      const float v = row[j];
+      if (v > best || (v == best && j < bi)) { best = v; bi = j; }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

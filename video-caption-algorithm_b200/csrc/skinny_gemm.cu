@@ -55,11 +55,15 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// grid = (N/64, ksplit, ceil(M/64)), block = 128
-__global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ W,
+// grid = (N/64, ksplit, ceil(M/64)), block = 128.  STAGE: the activation slice (64 rows x kslice) is copied to shared
+// memory once per CTA (asynchronous 16-byte copies, all in flight together) instead of each warp pulling its B fragments
+// through L1 batch by batch: one memory round trip for x instead of one per 64-k batch.
+// The weight rows are constants, so the first two register batches are requested BEFORE griddepcontrol.wait: they stream
+// in from HBM while the previous kernel of the chain is still running.
+template <bool STAGE>
+__global__ void __launch_bounds__(SK_WARPS * 32, 3) skinny_gemm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ W,
                                                                    float* __restrict__ P, int M, int N, int K, int kslice) {
-  pdl_wait();
-  pdl_launch_dependents();
+  extern __shared__ __align__(16) uint8_t sk_xs[];       // STAGE: 64 rows, pitch kslice*2 + 64 bytes
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int f0 = blockIdx.x * SK_BN + warp * 16;
@@ -67,18 +71,6 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const __nv_b
   const int m0 = blockIdx.z * SK_MT;
   const __nv_bfloat16* w_lo = W + static_cast<size_t>(f0 + g) * K + k0 + 8 * t;        // feature row g
   const __nv_bfloat16* w_hi = w_lo + static_cast<size_t>(8) * K;                        // feature row g+8
-  // activation rows for this lane's B fragments: sequence m0 + nt*8 + g (clamped; masked at the store)
-  const __nv_bfloat16* xrow[8];
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    int m = m0 + nt * 8 + g;
-    m = m < M ? m : M - 1;
-    xrow[nt] = x + static_cast<size_t>(m) * K + k0 + 8 * t;
-  }
-  float acc[8][4];
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-
   const int nb = kslice / SK_KB;
   // two register buffers with compile-time names (A/B) so nothing lands in local memory
   uint4 wA[4], wB[4];   // {lo step0, hi step0, lo step1, hi step1}
@@ -88,26 +80,56 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const __nv_b
     w[0] = ldg_stream(w_lo + o, pol);      w[1] = ldg_stream(w_hi + o, pol);
     w[2] = ldg_stream(w_lo + o + 32, pol); w[3] = ldg_stream(w_hi + o + 32, pol);
   };
+  load(wA, 0);
+  if (nb > 1) load(wB, 1);
+  pdl_wait();
+  pdl_launch_dependents();
+  const int pitch = kslice * 2 + 64;
+  // activation rows for this lane's B fragments: sequence m0 + nt*8 + g (clamped; masked at the store)
+  const __nv_bfloat16* xrow[8];
+  if (STAGE) {
+    const int cpr = kslice >> 3;
+    for (int r = warp; r < SK_MT; r += SK_WARPS) {
+      int m = m0 + r;
+      m = m < M ? m : M - 1;
+      const uint4* src = reinterpret_cast<const uint4*>(x + static_cast<size_t>(m) * K + k0);
+      for (int col = lane; col < cpr; col += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sk_xs + r * pitch + col * 16)), "l"(src + col) : "memory");
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+  } else {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      int m = m0 + nt * 8 + g;
+      m = m < M ? m : M - 1;
+      xrow[nt] = x + static_cast<size_t>(m) * K + k0 + 8 * t;
+    }
+  }
+  float acc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+
   auto compute = [&](const uint4 (&w)[4], int b) {
 #pragma unroll
     for (int st = 0; st < 2; ++st) {
       const uint4 a = w[2 * st], c = w[2 * st + 1];
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-        const uint4 xb = __ldg(reinterpret_cast<const uint4*>(xrow[nt] + b * SK_KB + st * 32));
+        uint4 xb;
+        if (STAGE) xb = *reinterpret_cast<const uint4*>(sk_xs + (nt * 8 + g) * pitch + (b * SK_KB + st * 32 + 8 * t) * 2);
+        else xb = __ldg(reinterpret_cast<const uint4*>(xrow[nt] + b * SK_KB + st * 32));
         mma16816(acc[nt], a.x, c.x, a.y, c.y, xb.x, xb.y);     // slots from elements 0..3 of each 16-byte load
         mma16816(acc[nt], a.z, c.z, a.w, c.w, xb.z, xb.w);     // slots from elements 4..7
       }
     }
   };
-  load(wA, 0);
   for (int b = 0; b < nb; b += 2) {
-    const bool has1 = b + 1 < nb;
-    if (has1) load(wB, b + 1);
     compute(wA, b);
-    if (has1) {
-      if (b + 2 < nb) load(wA, b + 2);
+    if (b + 2 < nb) load(wA, b + 2);
+    if (b + 1 < nb) {
       compute(wB, b + 1);
+      if (b + 3 < nb) load(wB, b + 3);
     }
   }
   // C fragment: (feature f0+g, seq 2t,2t+1) and (feature f0+g+8, ...)
@@ -140,38 +162,38 @@ __device__ __forceinline__ float block_sum_small(float v, float* s_red) {
   return t;
 }
 constexpr int RL_MAX_KS = 64;
+constexpr int RL_BATCH = 12;            // partial loads in flight per thread
 __global__ void __launch_bounds__(256) resid_ln_kernel(float* __restrict__ h, const float* __restrict__ P, int ksplit,
                                                        const float* __restrict__ bias, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ xn, int rows, int dim,
                                                        float eps) {
   __shared__ float s_red[8];
+  const int row = blockIdx.x, c4 = threadIdx.x;          // blockDim.x == dim / 4
+  // parameters are constants: requested before the previous kernel of the chain has finished
+  const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+  const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+  const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + c4);
   pdl_wait();
   pdl_launch_dependents();
-  const int row = blockIdx.x, c4 = threadIdx.x;          // blockDim.x == dim / 4
   const size_t plane4 = static_cast<size_t>(rows) * dim / 4;
   const size_t o4 = static_cast<size_t>(row) * (dim / 4) + c4;
   float4 a = reinterpret_cast<const float4*>(h)[o4];
-  const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c4);
-  a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
   const float4* P4 = reinterpret_cast<const float4*>(P) + o4;
-  int s = 0;
-  for (; s + 4 <= ksplit; s += 4) {                      // fixed summation order, 4 loads in flight
-    const float4 p0 = P4[(s + 0) * plane4], p1 = P4[(s + 1) * plane4], p2 = P4[(s + 2) * plane4], p3 = P4[(s + 3) * plane4];
-    a.x += p0.x; a.y += p0.y; a.z += p0.z; a.w += p0.w;
-    a.x += p1.x; a.y += p1.y; a.z += p1.z; a.w += p1.w;
-    a.x += p2.x; a.y += p2.y; a.z += p2.z; a.w += p2.w;
-    a.x += p3.x; a.y += p3.y; a.z += p3.z; a.w += p3.w;
+  float4 acc = b;
+  for (int s0 = 0; s0 < ksplit; s0 += RL_BATCH) {        // fixed summation order, RL_BATCH loads in flight
+    float4 q[RL_BATCH];
+#pragma unroll
+    for (int i = 0; i < RL_BATCH; ++i)
+      if (s0 + i < ksplit) q[i] = P4[(s0 + i) * plane4];
+#pragma unroll
+    for (int i = 0; i < RL_BATCH; ++i)
+      if (s0 + i < ksplit) { acc.x += q[i].x; acc.y += q[i].y; acc.z += q[i].z; acc.w += q[i].w; }
   }
-  for (; s < ksplit; ++s) {
-    const float4 p = P4[s * plane4];
-    a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
-  }
+  a.x += acc.x; a.y += acc.y; a.z += acc.z; a.w += acc.w;
   reinterpret_cast<float4*>(h)[o4] = a;
   const float mean = block_sum_small((a.x + a.y) + (a.z + a.w), s_red) / static_cast<float>(dim);
   const float dx = a.x - mean, dy = a.y - mean, dz = a.z - mean, dw = a.w - mean;
   const float rstd = rsqrtf(block_sum_small((dx * dx + dy * dy) + (dz * dz + dw * dw), s_red) / static_cast<float>(dim) + eps);
-  const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
-  const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + c4);
   uint2 w;
   w.x = pack_bf16(dx * rstd * gm.x + bt.x, dy * rstd * gm.y + bt.y);
   w.y = pack_bf16(dz * rstd * gm.z + bt.z, dw * rstd * gm.w + bt.w);
@@ -181,16 +203,22 @@ __global__ void __launch_bounds__(256) resid_ln_kernel(float* __restrict__ h, co
 // out[m][n] = bf16(act(bias[n] + sum_s P[s][m][n]))
 __global__ void __launch_bounds__(256) bias_act_kernel(const float* __restrict__ P, int ksplit, const float* __restrict__ bias,
                                                        __nv_bfloat16* __restrict__ out, int M, int N, int gelu) {
-  pdl_wait();
-  pdl_launch_dependents();
   const size_t i4 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const size_t total4 = static_cast<size_t>(M) * N / 4;
-  if (i4 >= total4) return;
   const int n4 = static_cast<int>(i4 % (N / 4));
-  float4 a = __ldg(reinterpret_cast<const float4*>(bias) + n4);
-  for (int s = 0; s < ksplit; ++s) {
-    const float4 p = *(reinterpret_cast<const float4*>(P) + s * total4 + i4);
-    a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i4 < total4) a = __ldg(reinterpret_cast<const float4*>(bias) + n4);     // constant: before the wait
+  pdl_wait();
+  pdl_launch_dependents();
+  if (i4 >= total4) return;
+  for (int s0 = 0; s0 < ksplit; s0 += 8) {               // fixed order, 8 loads in flight
+    float4 q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (s0 + i < ksplit) q[i] = *(reinterpret_cast<const float4*>(P) + (s0 + i) * total4 + i4);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (s0 + i < ksplit) { a.x += q[i].x; a.y += q[i].y; a.z += q[i].z; a.w += q[i].w; }
   }
   if (gelu) { a.x = gelu_tanh(a.x); a.y = gelu_tanh(a.y); a.z = gelu_tanh(a.z); a.w = gelu_tanh(a.w); }
   uint2 w;
@@ -219,9 +247,17 @@ int skinny_gemm(const void* x, const void* W, float* P, int M, int N, int K, int
   VC_REQUIRE(M > 0 && N % SK_BN == 0 && K % SK_KB == 0, "skinny_gemm: M=%d N=%d (%%64) K=%d (%%64)", M, N, K);
   VC_REQUIRE(ksplit >= 1 && (K / SK_KB) % ksplit == 0, "skinny_gemm: ksplit=%d does not divide K/64=%d", ksplit, K / SK_KB);
   dim3 grid(N / SK_BN, ksplit, (M + SK_MT - 1) / SK_MT);
-  VC_LAUNCH("skinny_gemm", static_cast<double>(N) * K * 2.0, s,
-            VC_CUDA_OK(launch_pdl(skinny_gemm_kernel, grid, dim3(SK_WARPS * 32), 0, s, static_cast<const __nv_bfloat16*>(x),
-                                  static_cast<const __nv_bfloat16*>(W), P, M, N, K, K / ksplit)));
+  const int kslice = K / ksplit;
+  if (kslice <= 256) {
+    const size_t smem = static_cast<size_t>(SK_MT) * (kslice * 2 + 64);
+    VC_LAUNCH("skinny_gemm", static_cast<double>(N) * K * 2.0, s,
+              VC_CUDA_OK(launch_pdl(skinny_gemm_kernel<true>, grid, dim3(SK_WARPS * 32), smem, s, static_cast<const __nv_bfloat16*>(x),
+                                    static_cast<const __nv_bfloat16*>(W), P, M, N, K, kslice)));
+  } else {
+    VC_LAUNCH("skinny_gemm", static_cast<double>(N) * K * 2.0, s,
+              VC_CUDA_OK(launch_pdl(skinny_gemm_kernel<false>, grid, dim3(SK_WARPS * 32), 0, s, static_cast<const __nv_bfloat16*>(x),
+                                    static_cast<const __nv_bfloat16*>(W), P, M, N, K, kslice)));
+  }
   VC_CUDA_OK(cudaGetLastError());
   return 0;
 }

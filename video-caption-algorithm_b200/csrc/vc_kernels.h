@@ -102,6 +102,12 @@ size_t decode_partial_floats_per_row(const VcGptWeights* w);
 int decode_steps(const VcGptWeights* w, const DecodeBuffers& b, const VcKvCache* cache, int n_seq, int past0, int n_steps, const float* emb,
                  const DecodeGreedy* greedy, float* logits, long long logits_step_stride, cudaStream_t stream);
 
+// decode_lean.cu — persistent decode kernel with symmetric warps (mma.sync + L2-staged partial sums), n_seq <= 64
+bool decode_lean_supported(const VcGptWeights* w, int n_seq, const VcKvCache* c);
+size_t decode_lean_partial_floats_per_row(const VcGptWeights* w);
+int decode_lean_steps(const VcGptWeights* w, const DecodeBuffers& b, float* logits_ws, const VcKvCache* cache, int n_seq, int past0, int n_steps,
+                      const float* emb, const DecodeGreedy* greedy, float* logits, long long logits_step_stride, cudaStream_t stream);
+
 // beam_kernels.cu
 int beam_step(const float* logits, long long ld, int vocab, int n_rows, int rows_per_item, const int32_t* seqs, int max_len, int cur_len,
               const float* running, float rep_penalty, int ngram, int min_new, int eos, int raw, int K, float* cand_score,

@@ -16,7 +16,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 SO_PATH = CSRC / "libvcb200.so"
-SOURCES = ["gemm_tcgen05.cu", "vit_kernels.cu", "vit_attention_tc.cu", "gpt2_kernels.cu", "skinny_gemm.cu", "decode_step.cu", "beam_kernels.cu", "c_abi.cu"]
+SOURCES = ["gemm_tcgen05.cu", "vit_kernels.cu", "vit_attention_tc.cu", "gpt2_kernels.cu", "skinny_gemm.cu", "decode_step.cu", "decode_lean.cu", "beam_kernels.cu", "c_abi.cu"]
 HEADERS = ["vc_common.cuh", "vc_kernels.h", "../../include/vcb200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
