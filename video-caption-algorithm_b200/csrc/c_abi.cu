@@ -82,7 +82,7 @@ struct GptBuffers {
   float* cand_v; int* cand_i; unsigned int* bar;
   size_t total;
 };
-constexpr int kDecodeMaxRows = 128;   // decode steps with more live sequences use the tcgen05 GEMM path
+constexpr int kDecodeMaxRows = 256;   // decode steps with more live sequences use the tcgen05 GEMM path
 static GptBuffers carve_gpt(const VcGptWeights* w, int n_seq, int max_rows, void* base) {
   const size_t R = static_cast<size_t>(max_rows);
   uint8_t* p = static_cast<uint8_t*>(base);

@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(128) gpt_attention_kernel(const __nv_bfloat16*
 // memory round trips instead of one per key.  Rows are padded to 144 B (conflict-free 16-byte reads).
 constexpr int ATT_SMEM_MAX_S = 256;
 constexpr int ATT_ROW_B = 144;
-__global__ void __launch_bounds__(128) gpt_attention_smem_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ P, int ksplit,
+__global__ void __maxnreg__(144) gpt_attention_smem_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ P, int ksplit,
                                                                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                                                                  __nv_bfloat16* __restrict__ kv, const int32_t* __restrict__ slot, int layer,
                                                                  int n_seq, int rows_total, int heads, int s_max, int L, int past_len) {

@@ -60,8 +60,10 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
 // through L1 batch by batch: one memory round trip for x instead of one per 64-k batch.
 // The weight rows are constants, so the first two register batches are requested BEFORE griddepcontrol.wait: they stream
 // in from HBM while the previous kernel of the chain is still running.
+// Register budget: the staged variant must fit beside an encoder GEMM CTA (448 threads x 104 registers leave 19K per SM),
+// so it is capped at 144 registers; the unstaged one (lm_head) only needs three CTAs per SM.
 template <bool STAGE>
-__global__ void __launch_bounds__(SK_WARPS * 32, 3) skinny_gemm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ W,
+__global__ void __maxnreg__(STAGE ? 144 : 168) skinny_gemm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ W,
                                                                    float* __restrict__ P, int M, int N, int K, int kslice) {
   extern __shared__ __align__(16) uint8_t sk_xs[];       // STAGE: 64 rows, pitch kslice*2 + 64 bytes
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -289,9 +289,9 @@ class B200CaptionModel:
             torch.cuda.nvtx.range_pop()
         return ids, lengths
 
-    def pipeline(self, max_new_tokens: int = 20, decode_group: int = 2) -> "CaptionPipeline":
+    def pipeline(self, max_new_tokens: int = 20, decode_group: int = 2, overlap_decode: bool = True) -> "CaptionPipeline":
         """Throughput path: a three-stream software pipeline over batches (see CaptionPipeline)."""
-        return CaptionPipeline(self, max_new_tokens, decode_group)
+        return CaptionPipeline(self, max_new_tokens, decode_group, overlap_decode)
 
     def caption_from_host(self, frames_u8_host: torch.Tensor, max_new_tokens: int = 20, num_beams: int = 1):
         """End-to-end call with HOST buffers: pinned uint8 frames -> H2D -> pipeline -> ids D2H.
@@ -316,7 +316,9 @@ class CaptionPipeline:
         ids, lens = pipe.result(t0)    # host int32 tensors (pinned); blocks until that batch is done
     """
 
-    def __init__(self, model: B200CaptionModel, max_new_tokens: int, decode_group: int = 2):
+    MAX_DECODE_ROWS = 256          # c_abi.cu kDecodeMaxRows: the weight-streaming decode step handles this many sequences
+
+    def __init__(self, model: B200CaptionModel, max_new_tokens: int, decode_group: int = 2, overlap_decode: bool = True):
         """decode_group: consecutive batches whose sequences are decoded together (group * batch <= 128).  The decode
         chain is latency-bound, not bandwidth-bound: 128 sequences cost about the same as 64, so decoding two encoder
         batches per chain halves the decode cost per batch.  Per-sequence results do not depend on the grouping."""
@@ -328,7 +330,7 @@ class CaptionPipeline:
         with torch.cuda.device(dev):
             self.copy_stream = torch.cuda.Stream(dev)
             self.enc_stream = torch.cuda.Stream(dev)
-            self.dec_stream = torch.cuda.Stream(dev, priority=-1)
+            self.dec_stream = torch.cuda.Stream(dev, priority=-1) if overlap_decode else self.enc_stream
         self._slots = [dict(frames=None, ids=None, lens=None, done=None, enc_done=None, h_ids=None, h_lens=None, prefix=None, cb=None, to_host=True)
                        for _ in range(self.depth)]
         self._pending: list = []       # tickets encoded but not yet decoded
@@ -361,7 +363,7 @@ class CaptionPipeline:
         self._pending.append(ticket)
         self._n += 1
         if self._pending and (len(self._pending) >= self.group or
-                              sum(self._slots[t % self.depth]["prefix"].shape[0] for t in self._pending) * 2 > 128):
+                              sum(self._slots[t % self.depth]["prefix"].shape[0] for t in self._pending) * 2 > self.MAX_DECODE_ROWS):
             self._flush()
         return ticket
 
