@@ -322,7 +322,7 @@ def run_b200(args):
                     "frac": round(achieved / pk["tf_sustained"], 4), "peak_source": pk["source"] + " sustained bf16 (kernel timed inside a long step)",
                     "frac_of_burst": round(achieved / pk["tf_burst"], 4), "launches": g_calls, "avg_launch_ms": round(g_ms / max(g_calls, 1), 4),
                     "flop_per_launch_avg": g_fl / max(g_calls, 1), "traffic": traffic,
-                    "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r1_gemm_traffic.json (launch mix of the first 4 layers)",
+                    "traffic_source": "ncu dram__bytes_read+write per launch averaged over the 49 GEMM launches of one encoder pass, profiles/r1_gemm_traffic.json",
                     "encoder_stage_tflops": round(enc_tflops, 1), "encoder_stage_frac": round(enc_tflops / pk["tf_sustained"], 4),
                     "encoder_gflop_per_frame_executed": round(VIT_GFLOP_PER_FRAME, 3),
                     "encoder_pruning": "last block: proj/MLP/attention for the class-token row only (-6.3 % of 35.126 GFLOP/frame)"}
