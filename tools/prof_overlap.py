@@ -77,3 +77,21 @@ for name, fn, reps in [("gemm gelu", load_gemm1, 60), ("gemm bias", load_gemm0, 
         d1.record()
     torch.cuda.synchronize()
     print(f"decode under a loop of {name:10s}: {d0.elapsed_time(d1):7.2f} ms (alone ~14.7)   load loop {e0.elapsed_time(e1):7.2f} ms")
+
+# ---- graph replay vs eager launches of the same chain under a GEMM loop
+for use_graph in (True, False):
+    for _ in range(2):
+        m.greedy_ids(prefix, None, n_new, use_graph=use_graph)
+    torch.cuda.synchronize()
+    e0, e1, d0, d1 = ev(), ev(), ev(), ev()
+    with torch.cuda.stream(E):
+        e0.record()
+        for _ in range(60):
+            load_gemm1(E.cuda_stream)
+        e1.record()
+    with torch.cuda.stream(D):
+        d0.record()
+        m.greedy_ids(prefix, None, n_new, use_graph=use_graph)
+        d1.record()
+    torch.cuda.synchronize()
+    print(f"decode ({'graph' if use_graph else 'eager'}) under a loop of gemm gelu: {d0.elapsed_time(d1):7.2f} ms   load loop {e0.elapsed_time(e1):7.2f} ms")

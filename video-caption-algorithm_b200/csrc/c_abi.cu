@@ -82,7 +82,7 @@ struct GptBuffers {
   float* cand_v; int* cand_i; unsigned int* bar;
   size_t total;
 };
-constexpr int kDecodeMaxRows = 256;   // decode steps with more live sequences use the tcgen05 GEMM path
+constexpr int kDecodeMaxRows = 1024;  // n_seq * new positions handled by the weight-streaming kernels; beyond: tcgen05 GEMM path
 static GptBuffers carve_gpt(const VcGptWeights* w, int n_seq, int max_rows, void* base) {
   const size_t R = static_cast<size_t>(max_rows);
   uint8_t* p = static_cast<uint8_t*>(base);
@@ -99,7 +99,7 @@ static GptBuffers carve_gpt(const VcGptWeights* w, int n_seq, int max_rows, void
   b.next = reinterpret_cast<int32_t*>(p + off);     off += align_up(static_cast<size_t>(n_seq) * 4, 1024);
   {
     // fp32 split-K partials of the decode step's GEMMs (widest product), per-CTA argmax candidates, grid barrier
-    const size_t rows = n_seq < kDecodeMaxRows ? n_seq : kDecodeMaxRows;
+    const size_t rows = R < static_cast<size_t>(kDecodeMaxRows) ? R : static_cast<size_t>(kDecodeMaxRows);
     const int H = w->dim;
     size_t m = std::max(decode_partial_floats_per_row(w), decode_lean_partial_floats_per_row(w));
     m = std::max(m, static_cast<size_t>(skinny_ksplit(3 * H, H)) * 3 * H);
@@ -268,20 +268,23 @@ int vc_linear_bias_f32(const float* x, const float* w, const float* b, float* y,
 
 size_t vc_gpt_workspace_bytes(const VcGptWeights* w, int n_seq, int max_new_rows) { return carve_gpt(w, n_seq, max_new_rows, nullptr).total; }
 
-// Decode step as a chain of small kernels (one new position per sequence, few rows): every product streams its weights
-// once through the split-K skinny kernel, partial sums are folded into the next kernel of the chain, and every kernel is
-// a programmatic dependent launch so its launch latency and ramp overlap the previous kernel's tail.
-static int gpt_step_skinny(const VcGptWeights* w, const float* embeds, int n_seq, int past_len, VcKvCache* cache, const GptBuffers& b,
+// Few-row forward (a decode step, or the prefill of a caption batch: n_seq * L <= 1024 rows) as a chain of small kernels:
+// every product streams its weights once through the split-K skinny kernel, partial sums are folded into the next kernel of
+// the chain, and every kernel is a programmatic dependent launch so its launch latency and ramp overlap the previous
+// kernel's tail.  None of these kernels needs a whole SM, so the chain runs beside the resident CTAs of the encoder GEMM
+// of the next batch (CaptionPipeline); the tcgen05 GEMM path below would wait for a free SM at every product.
+static int gpt_step_skinny(const VcGptWeights* w, const float* embeds, int n_seq, int L, int past_len, VcKvCache* cache, const GptBuffers& b,
                            float* logits_out, cudaStream_t s) {
-  const int H = w->dim, M = n_seq;
-  const int ks_attn = skinny_ksplit(3 * H, H), ks_ap = skinny_ksplit(H, H), ks_fc = skinny_ksplit(4 * H, H), ks_mp = skinny_ksplit(H, 4 * H);
+  const int H = w->dim, M = n_seq * L;
+  const int mt = (M + 63) / 64;
+  const int ks_attn = skinny_ksplit(3 * H, H, mt), ks_ap = skinny_ksplit(H, H, mt), ks_fc = skinny_ksplit(4 * H, H, mt), ks_mp = skinny_ksplit(H, 4 * H, mt);
   int e;
-  if ((e = gpt_add_pos(embeds, w->wpe, b.h, n_seq, 1, past_len, H, s))) return e;
+  if ((e = gpt_add_pos(embeds, w->wpe, b.h, n_seq, L, past_len, H, s))) return e;
   if ((e = layernorm_f32_bf16(b.h, w->layer[0].ln1_g, w->layer[0].ln1_b, b.xn, M, H, 1e-5f, s))) return e;
   for (int l = 0; l < w->layers; ++l) {
     const VcGptLayer& Ly = w->layer[l];
     if ((e = skinny_gemm(b.xn, Ly.attn_w, b.partial, M, 3 * H, H, ks_attn, s))) return e;
-    if ((e = gpt_attention(nullptr, b.partial, ks_attn, Ly.attn_b, b.att, cache, l, n_seq, 1, past_len, s))) return e;
+    if ((e = gpt_attention(nullptr, b.partial, ks_attn, Ly.attn_b, b.att, cache, l, n_seq, L, past_len, s))) return e;
     if ((e = skinny_gemm(b.att, Ly.aproj_w, b.partial, M, H, H, ks_ap, s))) return e;
     if ((e = resid_ln(b.h, b.partial, ks_ap, Ly.aproj_b, Ly.ln2_g, Ly.ln2_b, b.xn, M, H, 1e-5f, s))) return e;
     if ((e = skinny_gemm(b.xn, Ly.fc_w, b.partial, M, 4 * H, H, ks_fc, s))) return e;
@@ -292,8 +295,10 @@ static int gpt_step_skinny(const VcGptWeights* w, const float* embeds, int n_seq
     const float* nb = last ? w->lnf_b : w->layer[l + 1].ln1_b;
     if ((e = resid_ln(b.h, b.partial, ks_mp, Ly.mproj_b, ng, nb, b.xn, M, H, 1e-5f, s))) return e;
   }
-  // tied lm_head: one K slice, so the "partial" is the logits row itself
-  return skinny_gemm(b.xn, w->wte, logits_out, M, w->vocab_pad, H, 1, s);
+  // ln_f + tied lm_head on the last position of every sequence only (HF computes all positions; unused).  One K slice, so
+  // the "partial" is the logits row itself.
+  if (L > 1 && (e = layernorm_rows(b.h, L, L - 1, w->lnf_g, w->lnf_b, nullptr, b.xn, n_seq, H, 1e-5f, s))) return e;
+  return skinny_gemm(b.xn, w->wte, logits_out, n_seq, w->vocab_pad, H, 1, s);
 }
 
 // VC_DECODE_PERSISTENT=1 selects the single-launch cooperative decode kernel (decode_step.cu); measured on B200 it is
@@ -321,7 +326,7 @@ static int gpt_forward_impl(const VcGptWeights* w, const float* embeds, int n_se
     return decode_lean_steps(w, decode_buffers(b), b.logits, cache, n_seq, past_len, 1, embeds, nullptr, logits_out, 0, s);
   if (L == 1 && past_len >= 1 && use_persistent_decode() && decode_supported(w, n_seq, cache))
     return decode_steps(w, decode_buffers(b), cache, n_seq, past_len, 1, embeds, nullptr, logits_out, 0, s);
-  if (L == 1 && n_seq <= kDecodeMaxRows && w->vocab_pad % 64 == 0) return gpt_step_skinny(w, embeds, n_seq, past_len, cache, b, logits_out, s);
+  if (M <= kDecodeMaxRows && w->vocab_pad % 64 == 0) return gpt_step_skinny(w, embeds, n_seq, L, past_len, cache, b, logits_out, s);
   if ((e = gpt_add_pos(embeds, w->wpe, b.h, n_seq, L, past_len, H, s))) return e;
   for (int l = 0; l < w->layers; ++l) {
     const VcGptLayer& Ly = w->layer[l];

@@ -130,7 +130,7 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, uint8_t* stg
 
 template <int MODE>
 // 104 registers x 448 threads leave ~19K registers per SM: one CTA of the decode chain (skinny GEMM: 18.4K) fits beside this kernel
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(104)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(80)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles must sit on 1024-byte boundaries (same offsets in both CTAs of the pair)
@@ -284,6 +284,9 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
     std::lock_guard<std::mutex> lk(g_cfg_mu);
     if (!g_attr_set[MODE]) {
       VC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      // ask for the largest shared-memory carve-out, not the smallest that holds SMEM_BYTES: what is left over (~45 KB)
+      // is where the decode chain's CTAs of the previous batch run beside this kernel's resident CTAs (CaptionPipeline)
+      VC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       g_attr_set[MODE] = true;
     }
   }

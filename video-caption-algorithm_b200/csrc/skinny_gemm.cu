@@ -231,19 +231,22 @@ __global__ void __launch_bounds__(256) bias_act_kernel(const float* __restrict__
 
 }  // namespace
 
-// K-slices of a multiple of 64; aim for >= ~2 CTAs per SM without exploding the partial buffer.
-int skinny_ksplit(int N, int K) {
-  const int blocks = N / SK_BN;
+// K-slices of a multiple of 64; aim for >= ~200 CTAs (row tiles included) without exploding the partial buffer: the fp32
+// partials are written and read back through L2 once per slice, which is the dominant traffic of a step beyond 64 rows.
+// Slices stay <= 256 wide where possible so that the activation block is staged in shared memory.
+int skinny_ksplit(int N, int K, int row_tiles) {
+  const int blocks = (N / SK_BN) * (row_tiles > 0 ? row_tiles : 1);
   const int kb = K / SK_KB;
-  if (blocks >= 296) return 1;
+  if (N / SK_BN >= 296) return 1;
   int best = 1;
   for (int ks = 1; ks <= kb; ++ks) {
     if (kb % ks) continue;
     best = ks;
-    if (blocks * ks >= 200) break;
+    if (blocks * ks >= 200 && K / ks <= 4 * SK_KB) break;
   }
   return best;
 }
+int skinny_ksplit(int N, int K) { return skinny_ksplit(N, K, 1); }
 
 int skinny_gemm(const void* x, const void* W, float* P, int M, int N, int K, int ksplit, cudaStream_t s) {
   VC_REQUIRE(M > 0 && N % SK_BN == 0 && K % SK_KB == 0, "skinny_gemm: M=%d N=%d (%%64) K=%d (%%64)", M, N, K);

@@ -72,6 +72,7 @@ int gpt_attention(const void* qkv, const float* P, int ksplit, const float* bias
 
 // skinny_gemm.cu (decode step, M <= 128)
 int skinny_ksplit(int N, int K);
+int skinny_ksplit(int N, int K, int row_tiles);   // fewer slices when the row tiles already supply the CTAs
 int skinny_gemm(const void* x, const void* W, float* P, int M, int N, int K, int ksplit, cudaStream_t s);
 int resid_ln(float* h, const float* P, int ksplit, const float* bias, const float* gamma, const float* beta, void* xn, int rows, int dim,
              float eps, cudaStream_t s);
