@@ -289,18 +289,19 @@ def test_engine_three_candidates_encode_once():
         InferenceEngine(InferenceConfig(device=DEV, backend="tensorrt"), state_dict=sd)
 
 
-def test_pipeline_equals_sequential_captions():
-    """CaptionPipeline (H2D / encode / decode of consecutive batches on three streams, two encoder batches per decode
+@pytest.mark.parametrize("group,overlap", [(2, True), (4, True), (2, False)])
+def test_pipeline_equals_sequential_captions(group, overlap):
+    """CaptionPipeline (H2D / encode / decode of consecutive batches on three streams, `group` encoder batches per decode
     chain) returns, for every batch, exactly the ids of the plain sequential call — device-resident and pinned-host inputs,
     more batches than pipeline slots, an odd batch left over at the end."""
     a, sd, m = _model("tiny")
-    batches = [synthetic.make_batch_u8(10 * i, 3, 2) for i in range(7)]
+    batches = [synthetic.make_batch_u8(10 * i, 3, 2) for i in range(2 * group + 3)]
     want = []
     for f in batches:
         ids, lens = m.caption_ids(f.to(DEV), max_new_tokens=6)
         torch.cuda.synchronize()
         want.append((ids.cpu().clone(), lens.cpu().clone()))
-    pipe = m.pipeline(max_new_tokens=6)
+    pipe = m.pipeline(max_new_tokens=6, decode_group=group, overlap_decode=overlap)
     tickets = []
     got = {}
     for i, f in enumerate(batches):

@@ -326,7 +326,9 @@ static int gpt_forward_impl(const VcGptWeights* w, const float* embeds, int n_se
     return decode_lean_steps(w, decode_buffers(b), b.logits, cache, n_seq, past_len, 1, embeds, nullptr, logits_out, 0, s);
   if (L == 1 && past_len >= 1 && use_persistent_decode() && decode_supported(w, n_seq, cache))
     return decode_steps(w, decode_buffers(b), cache, n_seq, past_len, 1, embeds, nullptr, logits_out, 0, s);
-  if (M <= kDecodeMaxRows && w->vocab_pad % 64 == 0) return gpt_step_skinny(w, embeds, n_seq, L, past_len, cache, b, logits_out, s);
+  // VC_PREFILL_TCGEN05=1 (A/B switch, read per call): multi-position forwards take the tcgen05 GEMM path as before
+  const bool chain_ok = L == 1 ? n_seq <= 256 || getenv("VC_PREFILL_TCGEN05") == nullptr : getenv("VC_PREFILL_TCGEN05") == nullptr;
+  if (chain_ok && M <= kDecodeMaxRows && w->vocab_pad % 64 == 0) return gpt_step_skinny(w, embeds, n_seq, L, past_len, cache, b, logits_out, s);
   if ((e = gpt_add_pos(embeds, w->wpe, b.h, n_seq, L, past_len, H, s))) return e;
   for (int l = 0; l < w->layers; ++l) {
     const VcGptLayer& Ly = w->layer[l];

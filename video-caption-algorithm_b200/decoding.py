@@ -15,6 +15,8 @@ from __future__ import annotations
 import ctypes as C
 from typing import List, Optional
 
+import os
+
 import torch
 
 from . import lib as L
@@ -76,9 +78,8 @@ def greedy_decode(m, prefix: torch.Tensor, prompt_ids: List[int], max_new: int, 
         enqueue()                              # eager warm-up (also sets func attributes outside capture)
         torch.cuda.current_stream().synchronize()
         g = torch.cuda.CUDAGraph()
-        # kernel nodes keep the priority of the stream they were captured on: capture on a high-priority stream so that the
-        # decode chain is scheduled ahead of the next batch's encoder CTAs when the two overlap (CaptionPipeline)
-        cap = torch.cuda.Stream(device=m.device, priority=-1)
+        # kernel nodes keep the priority of the stream they were captured on (model.decode_priority: equal to the encoder's)
+        cap = torch.cuda.Stream(device=m.device, priority=int(os.environ.get("VC_DECODE_PRIORITY", "0")))
         with torch.cuda.graph(g, stream=cap):
             enqueue()
         st[gkey] = g

@@ -25,6 +25,8 @@ import ctypes as C
 from dataclasses import dataclass, field
 from typing import List, Optional
 
+import os
+
 import torch
 
 from . import lib as L
@@ -302,11 +304,18 @@ class B200CaptionModel:
         return ids.cpu(), lengths.cpu()
 
 
+def decode_priority() -> int:
+    """Stream priority of the decode chain (and of its captured graph's kernel nodes).  Measured on B200 (tools/ab_pipeline.py):
+    the same priority as the encoder gives 47.0-47.6 ms per batch, a higher one 49.7 ms - a high-priority chain of ~2000
+    tiny kernels keeps interrupting the dispatch of the encoder's large grids.  VC_DECODE_PRIORITY overrides (0 or -1)."""
+    return int(os.environ.get("VC_DECODE_PRIORITY", "0"))
+
+
 class CaptionPipeline:
     """Batches in flight on three streams: H2D copy of batch i+2, preprocess + ViT encode + prefix of batch i+1, and the
     greedy decode of batch i.  The decode step is a chain of ~100 tiny latency-bound kernels that needs a few SM slots,
     the encoder is tensor-pipe bound; with the GEMM's shared-memory footprint cut to 161 KB the decode kernels of the
-    previous batch run underneath the encoder kernels of the next one (the decode stream has the higher priority), so
+    previous batches run underneath the encoder kernels of the next one (same stream priority, see decode_priority), so
     steady-state time per batch tends to the encoder time alone.  Results are bit-identical to `caption_ids`: the same
     kernels run on the same data, only on different streams.
 
@@ -319,9 +328,10 @@ class CaptionPipeline:
     MAX_DECODE_ROWS = 256          # c_abi.cu kDecodeMaxRows: the weight-streaming decode step handles this many sequences
 
     def __init__(self, model: B200CaptionModel, max_new_tokens: int, decode_group: int = 2, overlap_decode: bool = True):
-        """decode_group: consecutive batches whose sequences are decoded together (group * batch <= 128).  The decode
-        chain is latency-bound, not bandwidth-bound: 128 sequences cost about the same as 64, so decoding two encoder
-        batches per chain halves the decode cost per batch.  Per-sequence results do not depend on the grouping."""
+        """decode_group: consecutive batches whose sequences are decoded together (group * batch <= 256).  The decode
+        chain is mostly latency-bound: 20 tokens cost 10.1 ms for 64 sequences, 13.5 ms for 128, 19.4 ms for 256, so
+        decoding several encoder batches per chain cuts the decode cost per batch.  Per-sequence results do not depend
+        on the grouping.  overlap_decode=False runs the chain on the encoder's stream (no concurrency)."""
         self.m = model
         self.max_new = int(max_new_tokens)
         self.group = max(1, int(decode_group))
@@ -330,7 +340,7 @@ class CaptionPipeline:
         with torch.cuda.device(dev):
             self.copy_stream = torch.cuda.Stream(dev)
             self.enc_stream = torch.cuda.Stream(dev)
-            self.dec_stream = torch.cuda.Stream(dev, priority=-1) if overlap_decode else self.enc_stream
+            self.dec_stream = torch.cuda.Stream(dev, priority=decode_priority()) if overlap_decode else self.enc_stream
         self._slots = [dict(frames=None, ids=None, lens=None, done=None, enc_done=None, h_ids=None, h_lens=None, prefix=None, cb=None, to_host=True)
                        for _ in range(self.depth)]
         self._pending: list = []       # tickets encoded but not yet decoded
