@@ -32,7 +32,7 @@ int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* ptr, int rows, int K, int
 
 namespace {
 
-constexpr int AT_THREADS = 320;
+constexpr int AT_THREADS = 352;            // warp 0 TMA, warps 1 and 10 MMA issuers (one per query tile), warps 2-9 softmax
 constexpr int AT_MAX_EXTRA = 8;              // keys / query rows beyond 256 handled outside the MMA
 constexpr int AT_Q_TILE = 128 * 128;            // bytes: 128 rows x 64 dims bf16
 constexpr int AT_KV_MAX = 256 * 128;            // bytes reserved for K (and V): up to 256 keys
@@ -102,7 +102,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&qkv_full[i], 1); mbar_init(&qkv_empty[i], 1);
+      mbar_init(&qkv_full[i], 1); mbar_init(&qkv_empty[i], m_tiles);
       mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4);
     }
     fence_mbar_init();
@@ -134,19 +134,23 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       }
       __syncwarp();
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
-    constexpr uint64_t desc_hi = umma_desc_sw128_hi();
-    const uint32_t idesc_s = umma_idesc_bf16(128, NK);
-    const uint32_t idesc_pv = umma_idesc_bf16(128, 64) | (1u << 16);   // B (= V) is MN-major: [keys][64 dims]
-    const uint32_t smem_lo = (smem_u32(smem) & 0x3FFFFu) >> 4;
-    int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const uint32_t par_buf = (it >> 1) & 1, par = it & 1;
-      const uint32_t b_lo = smem_lo + buf * (AT_BUF >> 4);
-      mbar_wait(&qkv_full[buf], par_buf);
-      for (int t = 0; t < m_tiles; ++t) {
+  } else if (warp == 1 || warp == 10) {
+    // ------------------------------------------------ MMA issuers: one warp per query tile, so the two tiles of a (frame,
+    // head) are NOT in lockstep.  Tile 1 starts half a period late (after tile 0's first softmax) and stays there: while
+    // one tile's softmax warps own the MUFU pipes, the other tile is in its MMA / output / wait phases.
+    const int t = warp == 1 ? 0 : 1;
+    if (t < m_tiles && static_cast<int>(blockIdx.x) < n_items) {
+      constexpr uint64_t desc_hi = umma_desc_sw128_hi();
+      const uint32_t idesc_s = umma_idesc_bf16(128, NK);
+      const uint32_t idesc_pv = umma_idesc_bf16(128, 64) | (1u << 16);   // B (= V) is MN-major: [keys][64 dims]
+      const uint32_t smem_lo = (smem_u32(smem) & 0x3FFFFu) >> 4;
+      if (t == 1) mbar_wait(&p_full[0], 0);
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t par_buf = (it >> 1) & 1, par = it & 1;
+        const uint32_t b_lo = smem_lo + buf * (AT_BUF >> 4);
+        mbar_wait(&qkv_full[buf], par_buf);
         mbar_wait(&o_empty[t], par ^ 1);           // previous item's output of this tile has left TMEM
         tc_fence_after();
         if (elect_one()) {
@@ -157,8 +161,6 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           tc_commit(&s_full[t]);
         }
         __syncwarp();
-      }
-      for (int t = 0; t < m_tiles; ++t) {
         mbar_wait(&p_full[t], par);
         tc_fence_after();
         if (elect_one()) {
@@ -167,7 +169,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           for (int k = 0; k < ksteps; ++k)
             tc_mma_bf16_ts(tmem_base + t * 256 + 128, tmem_base + t * 256 + 8 * k, dv + 128 * k, idesc_pv, k != 0);
           tc_commit(&o_full[t]);
-          if (t == m_tiles - 1) tc_commit(&qkv_empty[buf]);   // every MMA that reads this buffer has retired
+          tc_commit(&qkv_empty[buf]);              // every MMA of this tile that reads the buffer has retired (count = tiles)
         }
         __syncwarp();
       }
