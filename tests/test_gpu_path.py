@@ -289,6 +289,32 @@ def test_engine_three_candidates_encode_once():
         InferenceEngine(InferenceConfig(device=DEV, backend="tensorrt"), state_dict=sd)
 
 
+def test_ragged_and_empty_batches():
+    """Odd shapes through the public call: one frame, batch sizes that are not multiples of anything, an empty batch, a
+    one-token and a long decode.  Every row of a ragged batch must equal the same video captioned alone (rows are
+    independent everywhere on the path)."""
+    a, sd, m = _model("tiny")
+    for B, T in [(1, 1), (3, 5), (5, 3)]:
+        f = synthetic.make_batch_u8(7, B, T).to(DEV)
+        ids, lens = m.caption_ids(f, max_new_tokens=5)
+        torch.cuda.synchronize()
+        assert ids.shape == (B, 5) and lens.shape == (B,)
+        for b in range(B):
+            i1, l1 = m.caption_ids(f[b:b + 1], max_new_tokens=5)
+            assert torch.equal(i1[0], ids[b]) and int(l1[0]) == int(lens[b])
+    empty = torch.zeros(0, 4, 224, 224, 3, dtype=torch.uint8, device=DEV)
+    ids, lens = m.caption_ids(empty, max_new_tokens=5)
+    assert ids.shape == (0, 5) and lens.shape == (0,)
+    feat = m.encoder(torch.zeros(0, 3, 4, 224, 224, device=DEV))
+    assert feat.shape == (0, a.video_dim)
+    f = synthetic.make_batch_u8(0, 2, 2).to(DEV)
+    i1, _ = m.caption_ids(f, max_new_tokens=1)
+    i64, l64 = m.caption_ids(f, max_new_tokens=64)
+    assert i1.shape == (2, 1) and i64.shape == (2, 64) and torch.equal(i64[:, :1], i1)
+    with pytest.raises(ValueError):
+        m.caption_ids(f.float(), max_new_tokens=2)                        # wrong dtype is refused, not converted
+
+
 @pytest.mark.parametrize("group,overlap", [(2, True), (4, True), (2, False)])
 def test_pipeline_equals_sequential_captions(group, overlap):
     """CaptionPipeline (H2D / encode / decode of consecutive batches on three streams, `group` encoder batches per decode

@@ -63,6 +63,8 @@ class _Encoder:
         d = m.dims
         video = video.to(device=m.device, dtype=torch.float32).contiguous()
         n = B * T
+        if n == 0:
+            return torch.zeros(B, d["video_dim"], device=m.device, dtype=torch.float32)
         patches = m.ws.patches(n)
         lib = L.load()
         L.check(lib.vc_patchify_f32(video.data_ptr(), patches.data_ptr(), n, H, W, d["patch"], d["k_pad"], L.current_stream()))
@@ -248,6 +250,8 @@ class B200CaptionModel:
         B, T, H, W, _ = frames_u8.shape
         d = self.dims
         n = B * T
+        if n == 0:         # empty batch (or no frames): empty outputs, like the reference's modules on a 0-row tensor
+            return (torch.zeros(B, d["video_dim"], device=self.device), torch.zeros(B, d["prefix_len"], d["gpt_dim"], device=self.device))
         lib = L.load()
         st = L.current_stream()
         patches = self.ws.patches(n)
@@ -279,6 +283,8 @@ class B200CaptionModel:
     def caption_ids(self, frames_u8: torch.Tensor, max_new_tokens: int = 20, num_beams: int = 1, prompt_ids=None, **hf_kwargs):
         """frames -> token ids.  num_beams == 1: benchmark greedy; > 1: HF beam search semantics."""
         feat, prefix = self.encode_prefix(frames_u8)
+        if prefix.shape[0] == 0:
+            return (torch.full((0, max_new_tokens), EOS, dtype=torch.int32, device=self.device), torch.zeros(0, dtype=torch.int32, device=self.device))
         torch.cuda.nvtx.range_push("GPT2_Decoder_Step")
         try:
             if num_beams == 1 and not hf_kwargs:
