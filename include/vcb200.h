@@ -97,6 +97,16 @@ int vc_prof_begin(void);
 int vc_prof_end(int max_rows, char* names /*[max_rows][48]*/, float* total_ms, int* calls, double* work);
 
 /* ---- a1  preprocessing: core/preprocessing/frame_loader.py:34-47 ------------------------ */
+/* a1' — frame resize.  Replaces `transforms.Resize((image_size, image_size))` applied to the PIL image of every frame
+ * (core/preprocessing/frame_loader.py:34-45; torchvision -> PIL.Image.resize(BILINEAR) -> Pillow ImagingResample, 8 bpc):
+ * antialiased separable bilinear resample, horizontal pass first, uint8 intermediate, 22-bit fixed-point weights.
+ * src_hwc: uint8 [n, in_h, in_w, 3]; dst_hwc: uint8 [n, out_h, out_w, 3]; scratch: uint8 [n, in_h, out_w, 3] (may be NULL
+ * when in_h == out_h).  kx/ky: int32 [out, ksize] weights, bounds: int32 [out, 2] = (first input index, taps), built on the
+ * host with Pillow's rule (video-caption-algorithm_b200/resample.py: pillow_bilinear_coeffs).  Byte-exact vs Pillow. */
+int vc_resize_bilinear_u8(const uint8_t* src_hwc, int n_frames, int in_h, int in_w, uint8_t* scratch, uint8_t* dst_hwc, int out_h, int out_w,
+                          const int32_t* kx, const int32_t* bounds_x, int ksize_x, const int32_t* ky, const int32_t* bounds_y, int ksize_y,
+                          vc_stream_t stream);
+
 /* uint8 HWC frames -> bf16 through the 3x256 LUT of ToTensor+Normalize.
  * layout 0: [n,3,H,W] (the reference tensor, bf16-rounded); layout 1: patch-major
  * [n*(H/p)*(W/p), k_pad] with column c*p*p + i*p + j — the A operand of the patch-embed GEMM. */

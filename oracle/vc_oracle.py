@@ -54,6 +54,65 @@ def normalize_lut() -> torch.Tensor:
     return v.view(1, 256).sub(mean).div(std).contiguous()
 
 
+def pillow_bilinear_coeffs(in_size: int, out_size: int):
+    """Pillow `precompute_coeffs` + `normalize_coeffs_8bpc` for the bilinear filter (src/libImaging/Resample.c; Pillow 10.0.1
+    pinned in the reference's requirements.txt:70, 12.2.0 installed here — the routine is unchanged between them).
+    Support = max(in/out, 1) (antialiasing when shrinking); per output index a window [xmin, xmin+n) and weights
+    normalised in double precision, then rounded to 22 fractional bits.  -> (int weights [out][ksize], (xmin, n) [out])."""
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    weights, bounds = [], []
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = int(center - support + 0.5)
+        xmin = 0 if xmin < 0 else xmin
+        xmax = int(center + support + 0.5)
+        xmax = in_size if xmax > in_size else xmax
+        n = xmax - xmin
+        k, ww = [], 0.0
+        for x in range(n):
+            v = (x + xmin - center + 0.5) * (1.0 / filterscale)
+            v = -v if v < 0.0 else v
+            w = 1.0 - v if v < 1.0 else 0.0
+            k.append(w)
+            ww += w
+        if ww != 0.0:
+            k = [w / ww for w in k]
+        k += [0.0] * (ksize - n)
+        weights.append([int(-0.5 + w * (1 << 22)) if w < 0 else int(0.5 + w * (1 << 22)) for w in k])
+        bounds.append((xmin, n))
+    return weights, bounds
+
+
+def resize_bilinear_u8(frames_hwc: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
+    """frame_loader.py:36 `transforms.Resize((image_size, image_size))` on a PIL RGB image = PIL.Image.resize(BILINEAR) =
+    Pillow ImagingResample (8 bpc): horizontal pass, uint8 intermediate, vertical pass; each output byte is
+    clip8((2^21 + sum in*w) >> 22) in integer arithmetic.  uint8 [...,H,W,3] -> uint8 [...,out_h,out_w,3]."""
+    x = frames_hwc.to(torch.int64)
+    H, W = x.shape[-3], x.shape[-2]
+    if W != out_w:
+        wts, bnd = pillow_bilinear_coeffs(W, out_w)
+        cols = []
+        for xo in range(out_w):
+            xmin, n = bnd[xo]
+            k = torch.tensor(wts[xo][:n], dtype=torch.int64).view(n, 1)
+            acc = (x[..., xmin:xmin + n, :] * k).sum(dim=-2) + (1 << 21)
+            cols.append((acc >> 22).clamp_(0, 255))
+        x = torch.stack(cols, dim=-2)
+    if H != out_h:
+        wts, bnd = pillow_bilinear_coeffs(H, out_h)
+        rows = []
+        for yo in range(out_h):
+            ymin, n = bnd[yo]
+            k = torch.tensor(wts[yo][:n], dtype=torch.int64).view(n, 1, 1)
+            acc = (x[..., ymin:ymin + n, :, :] * k).sum(dim=-3) + (1 << 21)
+            rows.append((acc >> 22).clamp_(0, 255))
+        x = torch.stack(rows, dim=-3)
+    return x.to(torch.uint8)
+
+
 def preprocess_u8(frames_hwc: torch.Tensor) -> torch.Tensor:
     """uint8 [...,H,W,3] (already image_size x image_size, so Resize is the
     identity: frame_loader.py:36, PIL returns a copy) -> fp32 [...,3,H,W]."""

@@ -317,3 +317,23 @@ def test_beam_reorder_is_index_select(lib):
     ref = torch.full((n_seq, s_max), -1, dtype=torch.int32)
     ref[:, :upto] = slot_in[src.long(), :upto]
     assert torch.equal(out.cpu(), ref)
+
+
+def test_resize_byte_exact_vs_pillow_golden_and_oracle(lib, golden_dir):
+    """vc_resize_bilinear_u8 against the reference's PIL resize (golden fixtures) and against the oracle on fresh frames:
+    batched, odd sizes, row counts that are not multiples of the CTA's row group, upscaling — byte for byte."""
+    import numpy as np
+    from vcb200.resample import FrameResizer
+    rs = FrameResizer(DEV, 224, 224)
+    z = np.load(golden_dir / "resize.npz")
+    for k in [k for k in z.files if k.startswith("src_")]:
+        got = rs(torch.from_numpy(z[k]).to(DEV))
+        assert torch.equal(got.cpu(), torch.from_numpy(z["dst_" + k[4:]])), k
+    g = torch.Generator().manual_seed(3)
+    for shape in [(3, 2, 97, 131, 3), (1, 360, 480, 3), (5, 224, 321, 3), (2, 333, 224, 3), (2, 50, 40, 3)]:
+        x = torch.randint(0, 256, shape, generator=g, dtype=torch.uint8)
+        got = rs(x.to(DEV))
+        assert got.shape == shape[:-3] + (224, 224, 3)
+        assert torch.equal(got.cpu(), O.resize_bilinear_u8(x, 224, 224)), shape
+    x = torch.randint(0, 256, (2, 224, 224, 3), generator=g, dtype=torch.uint8)
+    assert torch.equal(rs(x.to(DEV)).cpu(), x)

@@ -289,6 +289,18 @@ def test_engine_three_candidates_encode_once():
         InferenceEngine(InferenceConfig(device=DEV, backend="tensorrt"), state_dict=sd)
 
 
+def test_frames_of_any_size_are_resized_like_the_reference():
+    """Frames that are not image_size x image_size go through the device resize (frame_loader.py:36) and then give exactly
+    the ids of the same frames resized by the oracle's Pillow restatement first."""
+    a, sd, m = _model("tiny")
+    g = torch.Generator().manual_seed(21)
+    raw = torch.randint(0, 256, (3, 4, 180, 240, 3), generator=g, dtype=torch.uint8)
+    ids, lens = m.caption_ids(raw.to(DEV), max_new_tokens=5)
+    pre = O.resize_bilinear_u8(raw, 224, 224)
+    ids2, lens2 = m.caption_ids(pre.to(DEV), max_new_tokens=5)
+    assert torch.equal(ids, ids2) and torch.equal(lens, lens2)
+
+
 def test_ragged_and_empty_batches():
     """Odd shapes through the public call: one frame, batch sizes that are not multiples of anything, an empty batch, a
     one-token and a long decode.  Every row of a ragged batch must equal the same video captioned alone (rows are

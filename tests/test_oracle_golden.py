@@ -65,3 +65,19 @@ def test_beam_search_matches_hf_generate(golden_dir, arch, key, nb, mx):
         n = int(lengths[b])
         assert ids[b, :n].tolist() == ref[b, :n].tolist()
         assert all(t == 50256 for t in ref[b, n:].tolist())
+
+
+def test_resize_matches_pillow_golden(golden_dir):
+    """oracle.resize_bilinear_u8 == the reference's transforms.Resize((224,224)) on PIL images (fixtures written by
+    oracle/pin_resize_against_pillow.py), byte for byte: shrinking (antialiased), growing, mixed, near-identity sizes."""
+    import numpy as np
+    z = np.load(golden_dir / "resize.npz")
+    names = [k for k in z.files if k.startswith("src_")]
+    assert len(names) >= 5
+    for k in names:
+        src, want = torch.from_numpy(z[k]), torch.from_numpy(z["dst_" + k[4:]])
+        got = O.resize_bilinear_u8(src, 224, 224)
+        assert torch.equal(got, want), k
+    # identity size is a copy
+    x = torch.randint(0, 256, (2, 224, 224, 3), dtype=torch.uint8)
+    assert torch.equal(O.resize_bilinear_u8(x, 224, 224), x)

@@ -165,6 +165,11 @@ int vc_prof_end(int max_rows, char* names, float* total_ms, int* calls, double* 
   return n;
 }
 
+int vc_resize_bilinear_u8(const uint8_t* src_hwc, int n_frames, int in_h, int in_w, uint8_t* scratch, uint8_t* dst_hwc, int out_h, int out_w,
+                          const int32_t* kx, const int32_t* bounds_x, int ksize_x, const int32_t* ky, const int32_t* bounds_y, int ksize_y,
+                          vc_stream_t stream) {
+  return resize_bilinear_u8(src_hwc, n_frames, in_h, in_w, scratch, dst_hwc, out_h, out_w, kx, bounds_x, ksize_x, ky, bounds_y, ksize_y, S(stream));
+}
 int vc_preprocess_u8(const uint8_t* frames_hwc, const float* lut3x256, void* out_bf16, int n_frames, int H, int W, int layout,
                      int patch, int k_pad, vc_stream_t stream) {
   return preprocess_u8(frames_hwc, lut3x256, out_bf16, n_frames, H, W, layout, patch, k_pad, S(stream));

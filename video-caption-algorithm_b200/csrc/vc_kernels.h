@@ -31,6 +31,10 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// resize_kernels.cu — Pillow-exact antialiased bilinear resize (uint8 HWC), coefficient tables from the host
+int resize_bilinear_u8(const uint8_t* src, int n, int H, int W, uint8_t* tmp, uint8_t* dst, int OH, int OW, const int32_t* kx, const int32_t* bx,
+                       int ksize_x, const int32_t* ky, const int32_t* by, int ksize_y, cudaStream_t s);
+
 // gemm_tcgen05.cu
 int gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int K, int mode, void* out, int ldo,
               const float* aux, int rows_per_group, int max_ctas, cudaStream_t stream);

@@ -101,8 +101,9 @@ class InferenceEngine:
         return cls(config, **kw)
 
     def load_frames_dir(self, frames_dir: str) -> torch.Tensor:
-        """frame_loader.py:13-47 for frames that are already image_size x image_size (Resize is then the identity);
-        returns uint8 [1,T,H,W,3] on the device.  Arbitrary-size frames need the PIL-exact resize."""
+        """frame_loader.py:13-47: sample `num_frames` of the frame_*.jpg files, decode (PIL, host), and return uint8
+        [1,T,H,W,3] on the device at the files' own size; `encode_prefix` then applies the Pillow-exact resize to
+        image_size x image_size on the GPU (resample.py), ToTensor/Normalize and the patch layout."""
         from PIL import Image
         import numpy as np
         files = sorted(Path(frames_dir).glob("frame_*.jpg"))
@@ -113,8 +114,8 @@ class InferenceEngine:
         for p in picks:
             with Image.open(p) as im:
                 a = np.asarray(im.convert("RGB"))
-            if a.shape[:2] != (self.config.image_size, self.config.image_size):
-                raise ValueError(f"{p}: {a.shape[:2]} frames need the resize front end (not on this path yet)")
+            if frames and a.shape != tuple(frames[0].shape):
+                raise ValueError(f"{p}: frame size {a.shape[:2]} differs from {tuple(frames[0].shape[:2])} within one clip")
             frames.append(torch.from_numpy(a.copy()))
         return torch.stack(frames).unsqueeze(0).to(self.model.device)
 

@@ -16,7 +16,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 SO_PATH = CSRC / "libvcb200.so"
-SOURCES = ["gemm_tcgen05.cu", "vit_kernels.cu", "vit_attention_tc.cu", "gpt2_kernels.cu", "skinny_gemm.cu", "decode_step.cu", "decode_lean.cu", "beam_kernels.cu", "c_abi.cu"]
+SOURCES = ["gemm_tcgen05.cu", "vit_kernels.cu", "resize_kernels.cu", "vit_attention_tc.cu", "gpt2_kernels.cu", "skinny_gemm.cu", "decode_step.cu", "decode_lean.cu", "beam_kernels.cu", "c_abi.cu"]
 HEADERS = ["vc_common.cuh", "vc_kernels.h", "../../include/vcb200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -93,6 +93,7 @@ _SIGNATURES = {
     "vc_launch_count": (C.c_longlong, []),
     "vc_prof_begin": (_i, []),
     "vc_prof_end": (_i, [_i, _p, _p, _p, _p]),
+    "vc_resize_bilinear_u8": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _p, _p, _i, _p]),
     "vc_preprocess_u8": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "vc_patchify_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "vc_gemm_bf16": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p]),

@@ -30,6 +30,7 @@ import os
 import torch
 
 from . import lib as L
+from .resample import FrameResizer
 from .memory import KvCache, Workspace
 from .packing import PackedModel, pack
 
@@ -210,6 +211,8 @@ class B200CaptionModel:
         self.ln_scale, self.in_weight = float(ln_scale), float(in_weight)
         self.chunk_frames = int(chunk_frames)
         self.ws = Workspace(self)
+        self.image_size = int(round((self.dims["tokens"] - 1) ** 0.5)) * self.dims["patch"]     # 224 for B/16 and L/14
+        self.resizer = FrameResizer(self.device, self.image_size, self.image_size)
         self.encoder = _Encoder(self)
         self.proj = lambda x: x                                            # nn.Identity (caption_model.py:67)
         self.decoder = _Decoder(self, tokenizer)
@@ -247,8 +250,11 @@ class B200CaptionModel:
         if frames_u8.device != self.device:
             raise ValueError("frames must already live on the model's device (use caption_from_host for host buffers)")
         frames_u8 = frames_u8.contiguous()
-        B, T, H, W, _ = frames_u8.shape
         d = self.dims
+        if frames_u8.numel() > 0 and tuple(frames_u8.shape[2:4]) != (self.image_size, self.image_size):
+            # transforms.Resize((image_size, image_size)) of frame_loader.py:36 — byte-exact with the PIL path, on the device
+            frames_u8 = self.resizer(frames_u8)
+        B, T, H, W, _ = frames_u8.shape
         n = B * T
         if n == 0:         # empty batch (or no frames): empty outputs, like the reference's modules on a 0-row tensor
             return (torch.zeros(B, d["video_dim"], device=self.device), torch.zeros(B, d["prefix_len"], d["gpt_dim"], device=self.device))
