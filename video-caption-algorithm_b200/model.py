@@ -435,6 +435,14 @@ class CaptionPipeline:
         self._flush()
         return self._last_done
 
+    def warm(self, frames_u8: torch.Tensor, after_decode=None) -> None:
+        """Run every decode-group size once (1..decode_group batches of this shape) so that all CUDA graphs, KV caches and
+        workspaces the steady state will need exist before the first timed / latency-sensitive batch."""
+        for g in range(1, self.group + 1):
+            for _ in range(g):
+                self.submit(frames_u8, to_host=False, after_decode=after_decode)
+            self.drain()
+
     def drain(self) -> None:
         self._flush()
         for s in (self.copy_stream, self.enc_stream, self.dec_stream):
