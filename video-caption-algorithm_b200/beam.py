@@ -5,10 +5,11 @@ Heavy work per step runs on the device through the C ABI: the GPT-2 forward over
 rows, log-softmax + RepetitionPenalty / NoRepeatNGram / MinNewTokens processors + running
 scores + the top-2*num_beams continuation search (`vc_beam_step`), and the KV-cache beam
 reorder as a slot-table update (`vc_beam_reorder`) instead of HF's per-layer index_select.
-What stays on the host is the bookkeeping over B x 2*num_beams candidates per step
-(transformers `_get_running_beams_for_next_iteration`, `_update_finished_beams`,
-`_check_early_stop_heuristic`) — a few hundred scalars, one small D2H/H2D
-pair per step (HF's own loop synchronises every step as well).
+The bookkeeping over B x 2*num_beams candidates per step (transformers
+`_get_running_beams_for_next_iteration`, `_update_finished_beams`, `_check_early_stop_heuristic`,
+SURVEY.md A.4) is a few hundred scalars: it stays in device tensors and is updated by small torch ops
+on the same stream, so a step has no host round trip (HF's own loop synchronises every step); the
+host reads the termination flag every fourth step.
 
 The prefill runs ONCE per video (B rows); the num_beams-fold replication HF performs is
 expressed through the slot table (every beam of a video reads the prompt positions from the
@@ -72,16 +73,22 @@ def beam_search_ids(m, prefix: torch.Tensor, prompt_ids: List[int], *, max_new_t
     x0 = torch.cat([prefix.to(device=dev, dtype=torch.float32), tok_emb.unsqueeze(0).expand(B, -1, -1)], dim=1).contiguous()
     L.check(lib.vc_gpt2_forward(gpt, x0.data_ptr(), B, L0, 0, C.byref(cache.c), ws.data_ptr(), ws.numel(), logits.data_ptr(), 0, st()))
 
-    # ---- host-side beam state (transformers `_beam_search` variable names in comments)
-    running_scores = torch.zeros(B, nb)
+    # ---- beam state ON THE DEVICE (transformers `_beam_search` variable names in comments): a few hundred scalars per
+    # step, updated with small torch ops on the same stream, so a step needs no host round trip.  The host looks at the
+    # termination flag every `check_every` steps; once the flag is up the finished-hypothesis state is frozen, so the
+    # steps that run past HF's stopping point change nothing.
+    check_every = 4
+    running_scores = torch.zeros(B, nb, device=dev)
     running_scores[:, 1:] = NEG
-    running_seqs = torch.full((B, nb, max_new_tokens), eos, dtype=torch.int64)
-    fin_seqs = running_seqs.clone()                       # sequences
-    fin_scores = torch.full((B, nb), NEG)                 # beam_scores
-    fin_done = torch.zeros(B, nb, dtype=torch.bool)       # is_sent_finished
-    fin_len = torch.zeros(B, nb, dtype=torch.int64)
-    unsatisfied = torch.ones(B, 1, dtype=torch.bool)      # is_early_stop_heuristic_unsatisfied
-    in_top = torch.arange(K).view(1, K) < nb              # top_num_beam_mask
+    running_seqs = torch.full((B, nb, max_new_tokens), eos, dtype=torch.int64, device=dev)
+    fin_seqs = running_seqs.clone()                                   # sequences
+    fin_scores = torch.full((B, nb), NEG, device=dev)                  # beam_scores
+    fin_done = torch.zeros(B, nb, dtype=torch.bool, device=dev)        # is_sent_finished
+    fin_len = torch.zeros(B, nb, dtype=torch.int64, device=dev)
+    unsatisfied = torch.ones(B, 1, dtype=torch.bool, device=dev)       # is_early_stop_heuristic_unsatisfied
+    in_top = (torch.arange(K, device=dev).view(1, K) < nb)             # top_num_beam_mask
+    row_base = (torch.arange(B, device=dev) * nb).view(B, 1)
+    stopped = torch.zeros((), dtype=torch.bool, device=dev)            # HF's loop would have ended before this step
     cur_len = 0
     while True:
         first = cur_len == 0
@@ -89,8 +96,8 @@ def beam_search_ids(m, prefix: torch.Tensor, prompt_ids: List[int], *, max_new_t
         L.check(lib.vc_beam_step(logits.data_ptr(), ld, V, rows, per_item, seqs_dev.data_ptr(), max_new_tokens, cur_len,
                                  run_dev.data_ptr(), float(repetition_penalty), int(no_repeat_ngram_size), int(min_new_tokens), eos, 0,
                                  K, cand_score.data_ptr(), cand_tok.data_ptr(), top_score.data_ptr(), top_idx.data_ptr(), st()))
-        top_scores = top_score.cpu()                      # the per-step sync (B x 2nb floats)
-        flat = top_idx.cpu().to(torch.int64)
+        top_scores = top_score
+        flat = top_idx.to(torch.int64)
         top_beam, top_tok = flat // V, flat % V
         cand_seqs = torch.gather(running_seqs, 1, top_beam.unsqueeze(-1).expand(-1, -1, max_new_tokens)).clone()
         cand_seqs[:, :, cur_len] = top_tok
@@ -108,22 +115,27 @@ def beam_search_ids(m, prefix: torch.Tensor, prompt_ids: List[int], *, max_new_t
         merged_scores = torch.cat([fin_scores, f_scores], dim=1)
         merged_seqs = torch.cat([fin_seqs, cand_seqs], dim=1)
         merged_done = torch.cat([fin_done, newly], dim=1)
-        merged_len = torch.cat([fin_len, torch.full((B, K), new_len, dtype=torch.int64)], dim=1)
-        fin_scores, sel = torch.topk(merged_scores, nb, dim=1)
-        fin_seqs = torch.gather(merged_seqs, 1, sel.unsqueeze(-1).expand(-1, -1, max_new_tokens))
-        fin_done = torch.gather(merged_done, 1, sel)
-        fin_len = torch.gather(merged_len, 1, sel)
+        merged_len = torch.cat([fin_len, torch.full((B, K), new_len, dtype=torch.int64, device=dev)], dim=1)
+        n_scores, sel = torch.topk(merged_scores, nb, dim=1)
+        n_seqs = torch.gather(merged_seqs, 1, sel.unsqueeze(-1).expand(-1, -1, max_new_tokens))
+        n_done = torch.gather(merged_done, 1, sel)
+        n_len = torch.gather(merged_len, 1, sel)
+        # freeze the finished state once HF's loop would have stopped
+        fin_scores = torch.where(stopped, fin_scores, n_scores)
+        fin_seqs = torch.where(stopped, fin_seqs, n_seqs)
+        fin_done = torch.where(stopped, fin_done, n_done)
+        fin_len = torch.where(stopped, fin_len, n_len)
         cur_len = new_len
         best_running = running_scores[:, :1] / (float(cur_len) ** length_penalty)
         worst_fin = torch.where(fin_done, fin_scores.min(dim=1, keepdim=True).values, torch.full_like(fin_scores, NEG))
         unsatisfied = unsatisfied & (best_running > worst_fin).any(dim=-1, keepdim=True)
-        if not (bool(unsatisfied.any()) and not bool(hit_stop.all())):
+        stopped = stopped | ~(unsatisfied.any() & ~hit_stop.all())
+        if cur_len >= max_new_tokens or (cur_len % check_every == 0 and bool(stopped)):      # the only host sync: every 4th step
             break
         # ---- next forward: reorder the cache by index, feed the chosen tokens
-        src_rows = (running_beam + torch.arange(B).view(B, 1) * nb).reshape(-1).to(torch.int32)
-        src_dev.copy_(src_rows, non_blocking=False)
-        tok_dev.copy_(running_tok.reshape(-1).to(torch.int32))
-        seqs_dev.copy_(running_seqs.reshape(n_rows, max_new_tokens).to(torch.int32))
+        src_dev.copy_((running_beam + row_base).reshape(-1))
+        tok_dev.copy_(running_tok.reshape(-1))
+        seqs_dev.copy_(running_seqs.reshape(n_rows, max_new_tokens))
         run_dev.copy_(running_scores.reshape(-1))
         past = L0 + cur_len - 1
         if not first:
@@ -134,12 +146,10 @@ def beam_search_ids(m, prefix: torch.Tensor, prompt_ids: List[int], *, max_new_t
         L.check(lib.vc_gpt2_embed_tokens(gpt, tok_dev.data_ptr(), n_rows, embeds.data_ptr(), st()))
         L.check(lib.vc_gpt2_forward(gpt, embeds.data_ptr(), n_rows, 1, past, C.byref(cache.c), ws.data_ptr(), ws.numel(),
                                     logits.data_ptr(), 0, st()))
-    ids = torch.full((B, max_new_tokens), eos, dtype=torch.int32)
     lengths = fin_len[:, 0].to(torch.int32)
-    for b in range(B):
-        n_tok = int(lengths[b])
-        ids[b, :n_tok] = fin_seqs[b, 0, :n_tok].to(torch.int32)
-    return ids.to(dev), lengths.to(dev)
+    pos = torch.arange(max_new_tokens, device=dev).view(1, -1)
+    ids = torch.where(pos < lengths.view(-1, 1), fin_seqs[:, 0, :], torch.full_like(fin_seqs[:, 0, :], eos)).to(torch.int32)
+    return ids, lengths
 
 
 def _greedy_with_processors(m, prefix, prompt_ids, max_new_tokens, ngram, rep_penalty, min_new, eos):
