@@ -337,3 +337,30 @@ def test_resize_byte_exact_vs_pillow_golden_and_oracle(lib, golden_dir):
         assert torch.equal(got.cpu(), O.resize_bilinear_u8(x, 224, 224)), shape
     x = torch.randint(0, 256, (2, 224, 224, 3), generator=g, dtype=torch.uint8)
     assert torch.equal(rs(x.to(DEV)).cpu(), x)
+
+
+def test_decode_chain_fused_fc_variant_matches(lib):
+    """skinny_gemm_gelu (fc1 + bias + gelu_new in one kernel, opt-in via VC_DECODE_FUSED_FC) against the default pair of
+    kernels through the public forward: same logits to fp32 summation-order noise."""
+    import os
+    from vcb200 import synthetic
+    from vcb200.model import B200CaptionModel
+    a = synthetic.ARCHS["tiny"]
+    m = B200CaptionModel(synthetic.make_state_dict(a, seed=1234), DEV, vit_heads=a.vit_heads, gpt_heads=a.gpt_heads)
+    g = torch.Generator().manual_seed(4)
+    prefix = (torch.randn(70, a.prefix_len, a.gpt_dim, generator=g) * 0.3).to(DEV)
+    forced = torch.randint(0, 50000, (70, 4), generator=g).int().to(DEV)
+    outs = []
+    for flag in (None, "1"):
+        if flag:
+            os.environ["VC_DECODE_FUSED_FC"] = flag
+        else:
+            os.environ.pop("VC_DECODE_FUSED_FC", None)
+        try:
+            ids, lens, lg = m.greedy_ids(prefix, None, 4, forced_ids=forced, keep_logits=True, use_graph=False)
+            torch.cuda.synchronize()
+            outs.append((ids.cpu().clone(), lg.float().cpu().clone()))
+        finally:
+            os.environ.pop("VC_DECODE_FUSED_FC", None)
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert (outs[0][1] - outs[1][1]).abs().max().item() < 2e-2

@@ -283,6 +283,10 @@ static int gpt_step_skinny(const VcGptWeights* w, const float* embeds, int n_seq
   const int H = w->dim, M = n_seq * L;
   const int mt = (M + 63) / 64;
   const int ks_attn = skinny_ksplit(3 * H, H, mt), ks_ap = skinny_ksplit(H, H, mt), ks_fc = skinny_ksplit(4 * H, H, mt), ks_mp = skinny_ksplit(H, 4 * H, mt);
+  // VC_DECODE_FUSED_FC=1 (A/B switch, read per call): fc1 with bias + gelu_new fused, K split inside the CTA.  Measured equal
+  // to the split-K product + bias_act pair (10.30 vs 10.13 ms per 20 tokens): what the saved launch gains, the whole-K
+  // activation block every CTA then pulls through L1 costs.
+  const bool fused_fc = H % 256 == 0 && getenv("VC_DECODE_FUSED_FC") != nullptr;
   int e;
   if ((e = gpt_add_pos(embeds, w->wpe, b.h, n_seq, L, past_len, H, s))) return e;
   if ((e = layernorm_f32_bf16(b.h, w->layer[0].ln1_g, w->layer[0].ln1_b, b.xn, M, H, 1e-5f, s))) return e;
@@ -292,8 +296,12 @@ static int gpt_step_skinny(const VcGptWeights* w, const float* embeds, int n_seq
     if ((e = gpt_attention(nullptr, b.partial, ks_attn, Ly.attn_b, b.att, cache, l, n_seq, L, past_len, s))) return e;
     if ((e = skinny_gemm(b.att, Ly.aproj_w, b.partial, M, H, H, ks_ap, s))) return e;
     if ((e = resid_ln(b.h, b.partial, ks_ap, Ly.aproj_b, Ly.ln2_g, Ly.ln2_b, b.xn, M, H, 1e-5f, s))) return e;
-    if ((e = skinny_gemm(b.xn, Ly.fc_w, b.partial, M, 4 * H, H, ks_fc, s))) return e;
-    if ((e = bias_act(b.partial, ks_fc, Ly.fc_b, b.hid, M, 4 * H, 1, s))) return e;
+    if (fused_fc) {
+      if ((e = skinny_gemm_gelu(b.xn, Ly.fc_w, Ly.fc_b, b.hid, M, 4 * H, H, s))) return e;
+    } else {
+      if ((e = skinny_gemm(b.xn, Ly.fc_w, b.partial, M, 4 * H, H, ks_fc, s))) return e;
+      if ((e = bias_act(b.partial, ks_fc, Ly.fc_b, b.hid, M, 4 * H, 1, s))) return e;
+    }
     if ((e = skinny_gemm(b.hid, Ly.mproj_w, b.partial, M, H, 4 * H, ks_mp, s))) return e;
     const bool last = l + 1 == w->layers;
     const float* ng = last ? w->lnf_g : w->layer[l + 1].ln1_g;

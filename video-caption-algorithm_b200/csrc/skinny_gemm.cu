@@ -150,6 +150,89 @@ __global__ void __maxnreg__(STAGE ? 144 : 168) skinny_gemm_kernel(const __nv_bfl
   }
 }
 
+// out[m][n] = bf16(gelu_new(bias[n] + sum_k x[m][k] W[n][k])) — the fc1 product of a decode step with its activation fused,
+// so the step has no separate bias+GELU kernel (one dependent launch less per layer).  GELU needs the complete sum, so K is
+// split across the four warps of a CTA (not across CTAs) and reduced through shared memory: grid = (N/16, 1, ceil(M/64)),
+// one 16-feature tile per CTA, warp kg owns K/4.  Small enough (128 threads, <= 144 registers, 17 KB) to run beside an
+// encoder GEMM CTA; the price is that every CTA pulls the whole activation block through L1 (~2 us of SM fill).
+constexpr int SKA_RED = 64 * 17;
+__global__ void __maxnreg__(144) skinny_gemm_gelu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ W,
+                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int M, int N, int K) {
+  __shared__ float s_red[SK_WARPS * SKA_RED];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int f0 = blockIdx.x * 16;
+  const int kq = K / SK_WARPS, k0 = warp * kq;
+  const int m0 = blockIdx.z * SK_MT;
+  const __nv_bfloat16* w_lo = W + static_cast<size_t>(f0 + g) * K + k0 + 8 * t;
+  const __nv_bfloat16* w_hi = w_lo + static_cast<size_t>(8) * K;
+  const int nb = kq / SK_KB;
+  uint4 wA[4], wB[4];
+  const uint64_t pol = l2_evict_first_policy();
+  auto load = [&](uint4 (&w)[4], int b) {
+    const int o = b * SK_KB;
+    w[0] = ldg_stream(w_lo + o, pol);      w[1] = ldg_stream(w_hi + o, pol);
+    w[2] = ldg_stream(w_lo + o + 32, pol); w[3] = ldg_stream(w_hi + o + 32, pol);
+  };
+  load(wA, 0);
+  if (nb > 1) load(wB, 1);
+  const int tid = threadIdx.x;
+  float bias_r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bias_r[i] = __ldg(bias + f0 + ((tid + i * 128) & 15));
+  pdl_wait();
+  pdl_launch_dependents();
+  const __nv_bfloat16* xrow[8];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    int m = m0 + nt * 8 + g;
+    m = m < M ? m : M - 1;
+    xrow[nt] = x + static_cast<size_t>(m) * K + k0 + 8 * t;
+  }
+  float acc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+  auto compute = [&](const uint4 (&w)[4], int b) {
+#pragma unroll
+    for (int st = 0; st < 2; ++st) {
+      const uint4 a = w[2 * st], c = w[2 * st + 1];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const uint4 xb = __ldg(reinterpret_cast<const uint4*>(xrow[nt] + b * SK_KB + st * 32));
+        mma16816(acc[nt], a.x, c.x, a.y, c.y, xb.x, xb.y);
+        mma16816(acc[nt], a.z, c.z, a.w, c.w, xb.z, xb.w);
+      }
+    }
+  };
+  for (int b = 0; b < nb; b += 2) {
+    compute(wA, b);
+    if (b + 2 < nb) load(wA, b + 2);
+    if (b + 1 < nb) {
+      compute(wB, b + 1);
+      if (b + 3 < nb) load(wB, b + 3);
+    }
+  }
+  float* rw = s_red + warp * SKA_RED;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int m = nt * 8 + 2 * t;
+    rw[m * 17 + g] = acc[nt][0];
+    rw[(m + 1) * 17 + g] = acc[nt][1];
+    rw[m * 17 + g + 8] = acc[nt][2];
+    rw[(m + 1) * 17 + g + 8] = acc[nt][3];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = tid + i * 128, m = idx >> 4, f = idx & 15;
+    if (m0 + m < M) {
+      const float* rr = s_red + m * 17 + f;
+      const float a = bias_r[i] + (((rr[0] + rr[SKA_RED]) + rr[2 * SKA_RED]) + rr[3 * SKA_RED]);      // fixed order
+      out[static_cast<size_t>(m0 + m) * N + f0 + f] = __float2bfloat16_rn(gelu_tanh(a));
+    }
+  }
+}
+
 // h[row] += bias + sum_s P[s][row];  xn[row] = LayerNorm(h[row]) (bf16).
 // One CTA per row, one float4 column per thread (dim/4 threads): the h load and all ksplit partial
 // loads of a thread are independent, so the whole row costs about one memory round trip.
@@ -263,6 +346,16 @@ int skinny_gemm(const void* x, const void* W, float* P, int M, int N, int K, int
               VC_CUDA_OK(launch_pdl(skinny_gemm_kernel<false>, grid, dim3(SK_WARPS * 32), 0, s, static_cast<const __nv_bfloat16*>(x),
                                     static_cast<const __nv_bfloat16*>(W), P, M, N, K, kslice)));
   }
+  VC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int skinny_gemm_gelu(const void* x, const void* W, const float* bias, void* out, int M, int N, int K, cudaStream_t s) {
+  VC_REQUIRE(M > 0 && N % 16 == 0 && K % (SK_WARPS * SK_KB) == 0, "skinny_gemm_gelu: M=%d N=%d (%%16) K=%d (%%256)", M, N, K);
+  dim3 grid(N / 16, 1, (M + SK_MT - 1) / SK_MT);
+  VC_LAUNCH("skinny_gemm_gelu", static_cast<double>(N) * K * 2.0, s,
+            VC_CUDA_OK(launch_pdl(skinny_gemm_gelu_kernel, grid, dim3(SK_WARPS * 32), 0, s, static_cast<const __nv_bfloat16*>(x),
+                                  static_cast<const __nv_bfloat16*>(W), bias, static_cast<__nv_bfloat16*>(out), M, N, K)));
   VC_CUDA_OK(cudaGetLastError());
   return 0;
 }

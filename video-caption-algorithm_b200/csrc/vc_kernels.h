@@ -75,6 +75,8 @@ int gpt_attention(const void* qkv, const float* P, int ksplit, const float* bias
                   int n_seq, int L, int past_len, cudaStream_t s);
 
 // skinny_gemm.cu (decode step, M <= 128)
+// out = bf16(gelu_new(x W^T + bias)), K split inside the CTA (no partial buffer); K % 256 == 0
+int skinny_gemm_gelu(const void* x_bf16, const void* w_bf16, const float* bias, void* out_bf16, int M, int N, int K, cudaStream_t s);
 int skinny_ksplit(int N, int K);
 int skinny_ksplit(int N, int K, int row_tiles);   // fewer slices when the row tiles already supply the CTAs
 int skinny_gemm(const void* x, const void* W, float* P, int M, int N, int K, int ksplit, cudaStream_t s);
