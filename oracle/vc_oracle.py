@@ -351,6 +351,22 @@ def apply_processors(scores: torch.Tensor, seqs: torch.Tensor, cur_len: int, *, 
     return scores
 
 
+def sample_warpers(scores: torch.Tensor, temperature: float, top_p: float) -> torch.Tensor:
+    """do_sample=True branch of text_decoder.py:131-144: transformers TemperatureLogitsWarper (`scores / temperature`) then
+    TopPLogitsWarper (generation/logits_process.py: sort ascending, cumulative softmax, remove while cumsum <= 1 - top_p,
+    keep at least the last = most probable token, scatter the mask back, fill with -inf).  The draw itself
+    (`torch.multinomial`) uses the framework RNG and is not part of the oracle."""
+    scores = scores / temperature
+    if top_p < 1.0:
+        sorted_logits, sorted_indices = torch.sort(scores, descending=False)
+        cumulative_probs = sorted_logits.softmax(dim=-1).cumsum(dim=-1)
+        sorted_indices_to_remove = cumulative_probs <= (1 - top_p)
+        sorted_indices_to_remove[..., -1:] = 0
+        indices_to_remove = sorted_indices_to_remove.scatter(1, sorted_indices, sorted_indices_to_remove)
+        scores = scores.masked_fill(indices_to_remove, float("-inf"))
+    return scores
+
+
 def beam_search(sd: dict, prefix: torch.Tensor, prompt_ids: torch.Tensor, *, num_beams: int, max_new_tokens: int,
                 no_repeat_ngram_size: int = 3, repetition_penalty: float = 1.1, min_new_tokens: int = 8,
                 length_penalty: float = 1.0, eos: int = 50256, heads: int = 12, step_logits_fn=None):

@@ -289,6 +289,40 @@ def test_engine_three_candidates_encode_once():
         InferenceEngine(InferenceConfig(device=DEV, backend="tensorrt"), state_dict=sd)
 
 
+def test_sampling_path_processors_warpers_and_draws():
+    """do_sample presets (text_decoder.py:137): the device-side processors and warpers equal the oracle's restatement of the
+    transformers classes on the same scores; a nucleus that keeps one token reproduces the greedy-with-processors ids; the
+    draw is reproducible under a seeded generator and never leaves the nucleus."""
+    from vcb200 import beam as BM
+    a, sd, m = _model("tiny")
+    g = torch.Generator().manual_seed(9)
+    V = a.vocab
+    logits = torch.randn(6, m.dims["vocab_pad"], generator=g) * 3
+    seqs = torch.randint(0, 40, (6, 12), generator=g).int()              # small alphabet: repeated tokens and repeated bigrams
+    for cur in (0, 1, 2, 5, 12):
+        want = O.apply_processors(logits[:, :V], seqs[:, :cur].long(), cur, repetition_penalty=1.05, no_repeat_ngram_size=3,
+                                  min_new_tokens=8, eos=50256)
+        got = BM._processed_scores(logits.to(DEV), seqs.to(DEV), cur, V, 3, 1.05, 8, 50256).cpu()
+        assert torch.equal(got, want), cur
+        w_want = O.sample_warpers(want, 0.9, 0.9)
+        w_got = BM._warped_scores(got.to(DEV), 0.9, 0.9).cpu()
+        assert torch.equal(torch.isinf(w_got), torch.isinf(w_want)) and torch.allclose(w_got[~torch.isinf(w_got)], w_want[~torch.isinf(w_want)])
+    prefix = (torch.randn(5, a.prefix_len, a.gpt_dim, generator=g) * 0.3).to(DEV)
+    kw = dict(max_new_tokens=10, num_beams=1, no_repeat_ngram_size=3, repetition_penalty=1.05, min_new_tokens=8)
+    ids_g, len_g = BM.beam_search_ids(m, prefix, [50256], **kw)
+    ids_1, len_1 = BM.beam_search_ids(m, prefix, [50256], do_sample=True, temperature=0.9, top_p=1e-6, **kw)    # nucleus of one token
+    assert torch.equal(ids_g, ids_1) and torch.equal(len_g, len_1)
+    gen = torch.Generator(device=DEV)
+    runs = []
+    for _ in range(2):
+        gen.manual_seed(123)
+        runs.append(BM.beam_search_ids(m, prefix, [50256], do_sample=True, temperature=0.9, top_p=0.9, generator=gen, **kw))
+    assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
+    assert int(runs[0][0].min()) >= 0 and int(runs[0][0].max()) < V
+    texts = m.decoder.generate(torch.randn(2, a.video_dim, device=DEV), prompt="", max_new_tokens=6, num_beams=1, temperature=0.9, top_p=0.9)
+    assert len(texts) == 2 and m.decoder.last_ids.shape == (2, 6)
+
+
 def test_frames_of_any_size_are_resized_like_the_reference():
     """Frames that are not image_size x image_size go through the device resize (frame_loader.py:36) and then give exactly
     the ids of the same frames resized by the oracle's Pillow restatement first."""

@@ -32,10 +32,11 @@ NEG = -1.0e9
 
 def beam_search_ids(m, prefix: torch.Tensor, prompt_ids: List[int], *, max_new_tokens: int, num_beams: int,
                     no_repeat_ngram_size: int = 3, repetition_penalty: float = 1.1, min_new_tokens: int = 8,
-                    length_penalty: float = 1.0, eos: int = EOS):
+                    length_penalty: float = 1.0, eos: int = EOS, do_sample: bool = False, temperature: float = 1.0, top_p: float = 1.0,
+                    generator=None):
     if num_beams == 1:
         return _greedy_with_processors(m, prefix, prompt_ids, max_new_tokens, no_repeat_ngram_size, repetition_penalty,
-                                       min_new_tokens, eos)
+                                       min_new_tokens, eos, do_sample=do_sample, temperature=temperature, top_p=top_p, generator=generator)
     d = m.dims
     dev = m.device
     lib = L.load()
@@ -152,9 +153,54 @@ def beam_search_ids(m, prefix: torch.Tensor, prompt_ids: List[int], *, max_new_t
     return ids, lengths
 
 
-def _greedy_with_processors(m, prefix, prompt_ids, max_new_tokens, ngram, rep_penalty, min_new, eos):
-    """HF greedy (`_sample` with do_sample=False): processors on the raw last-position logits, argmax,
-    finished rows emit pad(=eos), stop when every row has produced eos or at max_new_tokens."""
+def _processed_scores(logits: torch.Tensor, seqs: torch.Tensor, cur_len: int, V: int, ngram: int, rep_penalty: float, min_new: int,
+                      eos: int) -> torch.Tensor:
+    """transformers RepetitionPenalty -> NoRepeatNGram -> MinNewTokensLength processors on full rows, as device torch ops
+    (the sampling path needs the whole distribution; the argmax / beam paths use the fused `vc_beam_step` kernel).
+    `seqs` holds the generated tokens only: `generate(inputs_embeds=...)` starts from empty input_ids."""
+    scores = logits[:, :V].clone()
+    if cur_len > 0:
+        prev = seqs[:, :cur_len].to(torch.int64)
+        if rep_penalty != 1.0:
+            sc = torch.gather(scores, 1, prev)
+            pen = torch.full_like(sc, rep_penalty)          # tensor / tensor is an IEEE division; tensor / python-scalar on CUDA
+            sc = torch.where(sc < 0, sc * pen, sc / pen)    # multiplies by the rounded reciprocal (1 ulp off the CPU result)
+            scores.scatter_(1, prev, sc)
+        if ngram > 0 and cur_len + 1 >= ngram:
+            # ban every token that would complete an n-gram already present: windows whose first ngram-1 tokens equal the tail
+            n_win = cur_len - ngram + 1
+            if n_win > 0:
+                match = torch.ones(prev.shape[0], n_win, dtype=torch.bool, device=prev.device)
+                for j in range(ngram - 1):
+                    match &= prev[:, j:j + n_win] == prev[:, cur_len - (ngram - 1) + j].unsqueeze(1)
+                banned = prev[:, ngram - 1:ngram - 1 + n_win]
+                # a token can close a matching and a non-matching window: min-reduce so that one match is enough
+                val = torch.where(match, torch.full((), float("-inf"), device=scores.device), torch.full((), float("inf"), device=scores.device))
+                scores.scatter_reduce_(1, banned, val, reduce="amin", include_self=True)
+    if cur_len < min_new:
+        scores[:, eos] = float("-inf")
+    return scores
+
+
+def _warped_scores(scores: torch.Tensor, temperature: float, top_p: float) -> torch.Tensor:
+    """transformers TemperatureLogitsWarper then TopPLogitsWarper (min_tokens_to_keep=1): ascending sort, drop the tokens whose
+    cumulative probability stays <= 1 - top_p, always keep the most probable one."""
+    scores = scores / torch.full_like(scores[:, :1], float(temperature))
+    if top_p < 1.0:
+        srt, idx = torch.sort(scores, descending=False, dim=-1)
+        remove = srt.softmax(dim=-1).cumsum(dim=-1) <= (1.0 - float(top_p))
+        remove[:, -1:] = False
+        scores = scores.masked_fill(remove.scatter(1, idx, remove), float("-inf"))
+    return scores
+
+
+def _greedy_with_processors(m, prefix, prompt_ids, max_new_tokens, ngram, rep_penalty, min_new, eos, *, do_sample: bool = False,
+                            temperature: float = 1.0, top_p: float = 1.0, generator=None):
+    """HF `_sample`: processors on the raw last-position logits, then argmax (do_sample=False) or temperature / top-p warpers,
+    softmax and `torch.multinomial` (do_sample=True: text_decoder.py:137, presets "natural" / "safe_sample"); finished rows
+    emit pad(=eos); stop when every row has produced eos or at max_new_tokens.  All state stays on the device: the host reads
+    the all-finished flag every fourth step.  Sampling draws from torch's CUDA generator, so it is reproducible under
+    `torch.manual_seed` but is not comparable token-for-token with another implementation (excluded from parity)."""
     d = m.dims
     dev = m.device
     lib = L.load()
@@ -179,23 +225,27 @@ def _greedy_with_processors(m, prefix, prompt_ids, max_new_tokens, ngram, rep_pe
     L.check(lib.vc_gpt2_embed_tokens(gpt, prompt.data_ptr(), Lp, tok_emb.data_ptr(), st()))
     x0 = torch.cat([prefix.to(device=dev, dtype=torch.float32), tok_emb.unsqueeze(0).expand(B, -1, -1)], dim=1).contiguous()
     L.check(lib.vc_gpt2_forward(gpt, x0.data_ptr(), B, L0, 0, C.byref(cache.c), ws.data_ptr(), ws.numel(), logits.data_ptr(), 0, st()))
-    seqs = torch.full((B, max_new_tokens), eos, dtype=torch.int64)
-    unfinished = torch.ones(B, dtype=torch.bool)
-    lengths = torch.zeros(B, dtype=torch.int64)
+    unfinished = torch.ones(B, dtype=torch.bool, device=dev)
+    lengths = torch.zeros(B, dtype=torch.int32, device=dev)
+    eos_t = torch.full((B,), eos, dtype=torch.int32, device=dev)
     for cur_len in range(max_new_tokens):
-        L.check(lib.vc_beam_step(logits.data_ptr(), ld, V, B, 1, seqs_dev.data_ptr(), max_new_tokens, cur_len, 0, float(rep_penalty),
-                                 int(ngram), int(min_new), eos, 1, 1, cand_score.data_ptr(), cand_tok.data_ptr(), top_score.data_ptr(),
-                                 top_idx.data_ptr(), st()))
-        nxt = top_idx.cpu().to(torch.int64).view(-1)
-        nxt = torch.where(unfinished, nxt, torch.full_like(nxt, eos))
-        seqs[:, cur_len] = nxt
-        lengths += unfinished.long()
+        if do_sample:
+            scores = _processed_scores(logits, seqs_dev, cur_len, V, int(ngram), float(rep_penalty), int(min_new), eos)
+            scores = _warped_scores(scores, temperature, top_p)
+            nxt = torch.multinomial(scores.softmax(dim=-1), 1, generator=generator).view(-1).to(torch.int32)
+        else:
+            L.check(lib.vc_beam_step(logits.data_ptr(), ld, V, B, 1, seqs_dev.data_ptr(), max_new_tokens, cur_len, 0, float(rep_penalty),
+                                     int(ngram), int(min_new), eos, 1, 1, cand_score.data_ptr(), cand_tok.data_ptr(), top_score.data_ptr(),
+                                     top_idx.data_ptr(), st()))
+            nxt = top_idx.view(-1)
+        nxt = torch.where(unfinished, nxt, eos_t)
+        seqs_dev[:, cur_len] = nxt
+        lengths += unfinished.to(torch.int32)
         unfinished = unfinished & (nxt != eos)
-        if not bool(unfinished.any()) or cur_len + 1 == max_new_tokens:
+        if cur_len + 1 == max_new_tokens or ((cur_len + 1) % 4 == 0 and not bool(unfinished.any())):   # the only host sync
             break
-        seqs_dev.copy_(seqs.to(torch.int32))
-        tok_dev.copy_(nxt.to(torch.int32))
+        tok_dev.copy_(nxt)
         L.check(lib.vc_gpt2_embed_tokens(gpt, tok_dev.data_ptr(), B, embeds.data_ptr(), st()))
         L.check(lib.vc_gpt2_forward(gpt, embeds.data_ptr(), B, 1, L0 + cur_len, C.byref(cache.c), ws.data_ptr(), ws.numel(),
                                     logits.data_ptr(), 0, st()))
-    return seqs.to(torch.int32).to(dev), lengths.to(torch.int32).to(dev)
+    return seqs_dev, lengths

@@ -92,8 +92,9 @@ def greedy_decode(m, prefix: torch.Tensor, prompt_ids: List[int], max_new: int, 
 
 def hf_generate_ids(m, prefix: torch.Tensor, prompt_ids: List[int], *, max_new_tokens: int, num_beams: int = 1,
                     no_repeat_ngram_size: int = 3, repetition_penalty: float = 1.1, min_new_tokens: int = 8,
-                    length_penalty: float = 1.0):
+                    length_penalty: float = 1.0, do_sample: bool = False, temperature: float = 1.0, top_p: float = 1.0, generator=None):
     from .beam import beam_search_ids
     return beam_search_ids(m, prefix, prompt_ids, max_new_tokens=max_new_tokens, num_beams=num_beams,
                            no_repeat_ngram_size=no_repeat_ngram_size, repetition_penalty=repetition_penalty,
-                           min_new_tokens=min_new_tokens, length_penalty=length_penalty)
+                           min_new_tokens=min_new_tokens, length_penalty=length_penalty, do_sample=do_sample,
+                           temperature=temperature, top_p=top_p, generator=generator)

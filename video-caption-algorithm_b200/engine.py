@@ -128,10 +128,8 @@ class InferenceEngine:
         out = {}
         for key, prompt, preset in (("S1", cfg.prompt1, cfg.preset1), ("S2", cfg.prompt2, cfg.preset2), ("S3", cfg.prompt3, cfg.preset3)):
             kw = preset_to_kwargs(preset)
-            if kw["num_beams"] == 1 and kw["temperature"] != 1.0:
-                # nucleus-sampling presets draw from the torch RNG and are excluded from parity;
-                # this round they decode greedily with the same logits processors (next: §8f1)
-                kw["temperature"], kw["top_p"] = 1.0, 1.0
+            # nucleus-sampling presets (temperature != 1) draw from torch's CUDA generator on the device: reproducible under
+            # torch.manual_seed, excluded from token-for-token parity
             if prompt and m.decoder.tokenizer is None:
                 prompt = ""                                        # no BPE files offline: fall back to the bos prompt
             texts = m.decoder.generate(emb, prompt=prompt, **kw)

@@ -184,12 +184,10 @@ class _Decoder:
         B = emb.shape[0]
         prefix = self.mapper(emb).reshape(B, self.prefix_len, m.dims["gpt_dim"])
         do_sample = (num_beams == 1 and temperature != 1.0)               # text_decoder.py:137
-        if do_sample:
-            raise NotImplementedError("sampling presets use the torch RNG and are excluded from the B200 path this round")
         from .decoding import hf_generate_ids
         ids, lengths = hf_generate_ids(m, prefix, self._prompt_ids(prompt), max_new_tokens=max_new_tokens, num_beams=num_beams,
                                        no_repeat_ngram_size=no_repeat_ngram_size, repetition_penalty=repetition_penalty,
-                                       min_new_tokens=min_new_tokens)
+                                       min_new_tokens=min_new_tokens, do_sample=do_sample, temperature=temperature, top_p=top_p)
         self.last_ids, self.last_lengths = ids, lengths
         if self.tokenizer is None:
             return ["" for _ in range(B)]
