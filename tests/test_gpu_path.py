@@ -323,6 +323,37 @@ def test_sampling_path_processors_warpers_and_draws():
     assert len(texts) == 2 and m.decoder.last_ids.shape == (2, 6)
 
 
+def test_microbatcher_serves_concurrent_single_video_requests():
+    """serving.MicroBatcher: single-video requests from several threads (two frame sizes mixed) come back with exactly the
+    ids of the same video captioned alone, and they were served in fewer batches than requests."""
+    import threading
+    from vcb200.serving import MicroBatcher
+    a, sd, m = _model("tiny")
+    vids = [synthetic.make_batch_u8(100 + i, 1, 2)[0] for i in range(10)]                     # [T,224,224,3]
+    g = torch.Generator().manual_seed(2)
+    vids += [torch.randint(0, 256, (2, 120, 160, 3), generator=g, dtype=torch.uint8) for _ in range(4)]
+    want = []
+    for v in vids:
+        ids, lens = m.caption_ids(v.unsqueeze(0).to(DEV), max_new_tokens=5)
+        torch.cuda.synchronize()
+        want.append(ids[0, : int(lens[0])].tolist())
+    got = [None] * len(vids)
+    with MicroBatcher(m, max_batch=4, max_delay_ms=50.0, max_new_tokens=5) as mb:
+        def client(lo, hi):
+            futs = [(i, mb.submit(vids[i])) for i in range(lo, hi)]
+            for i, f in futs:
+                got[i] = f.result(timeout=120)[0]
+        ts = [threading.Thread(target=client, args=(k * 7, min(k * 7 + 7, len(vids)))) for k in range(2)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        with pytest.raises(ValueError):
+            mb.submit(torch.zeros(2, 224, 224, 3))                                             # not uint8
+    assert got == want
+    assert mb.served == len(vids) and mb.batches < len(vids)
+
+
 def test_frames_of_any_size_are_resized_like_the_reference():
     """Frames that are not image_size x image_size go through the device resize (frame_loader.py:36) and then give exactly
     the ids of the same frames resized by the oracle's Pillow restatement first."""

@@ -61,3 +61,11 @@ def test_synthetic_frames_are_reproducible_per_video_index():
     assert a.dtype == torch.uint8 and a.shape == (3, 4, 224, 224, 3)
     assert torch.equal(a[1], b[0])
     assert not torch.equal(a[0], a[1])
+
+
+def test_microbatcher_groups_requests_by_shape_in_arrival_order():
+    from vcb200.serving import group_requests
+    a, b = (8, 224, 224, 3), (8, 180, 240, 3)
+    assert group_requests([a, a, b, a, b], max_batch=2) == [[0, 1], [2, 4], [3]]
+    assert group_requests([], max_batch=4) == []
+    assert group_requests([a] * 5, max_batch=64) == [[0, 1, 2, 3, 4]]
