@@ -69,3 +69,17 @@ def test_microbatcher_groups_requests_by_shape_in_arrival_order():
     assert group_requests([a, a, b, a, b], max_batch=2) == [[0, 1], [2, 4], [3]]
     assert group_requests([], max_batch=4) == []
     assert group_requests([a] * 5, max_batch=64) == [[0, 1, 2, 3, 4]]
+
+
+def test_checkpoint_reader_unwraps_model_state(tmp_path):
+    import torch
+    from vcb200.engine import read_checkpoint
+    sd = {"a.weight": torch.randn(3, 2), "a.bias": torch.zeros(3)}
+    torch.save(sd, tmp_path / "raw.pt")
+    torch.save({"model_state": sd, "epoch": 3}, tmp_path / "wrapped.pt")
+    for name in ("raw.pt", "wrapped.pt"):
+        got = read_checkpoint(tmp_path / name)
+        assert set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+    torch.save({"epoch": 3}, tmp_path / "bad.pt")
+    with pytest.raises(ValueError):
+        read_checkpoint(tmp_path / "bad.pt")

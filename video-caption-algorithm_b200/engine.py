@@ -64,6 +64,17 @@ def preset_to_kwargs(name: str) -> dict:
     return dict(table.get(name, table["precise"]))
 
 
+def read_checkpoint(path) -> dict:
+    """core/models/model_loader.py:31-40, :73-75: a checkpoint file is either a raw state-dict or {"model_state": state-dict,
+    ...}; tensors only (loaded with weights_only=True — no pickled code is executed, unlike the reference's loader)."""
+    state = torch.load(Path(path), map_location="cpu", weights_only=True)
+    if isinstance(state, dict) and "model_state" in state:
+        state = state["model_state"]
+    if not isinstance(state, dict) or not all(isinstance(v, torch.Tensor) for v in state.values()):
+        raise ValueError(f"{path}: expected a state-dict of tensors (optionally under 'model_state')")
+    return state
+
+
 def load_caption_model(config: InferenceConfig, state_dict: Optional[dict] = None, tokenizer=None) -> B200CaptionModel:
     """The backend switch of core/models/model_loader.py:21-28 with one more value, "b200".
     `state_dict` may be passed directly (tests, benchmark); otherwise `config.ckpt` is loaded like
@@ -74,7 +85,7 @@ def load_caption_model(config: InferenceConfig, state_dict: Optional[dict] = Non
     if state_dict is None:
         if not config.ckpt:
             raise FileNotFoundError("InferenceConfig.ckpt is empty and no state_dict was given")
-        state_dict = torch.load(Path(config.ckpt), map_location="cpu", weights_only=True)
+        state_dict = read_checkpoint(config.ckpt)
     gelu = None if config.enable_mlp_bias_gelu_fusion else "erf"
     return B200CaptionModel(state_dict, config.device, vit_heads=_HEADS.get(config.vit_name, 12), gpt_heads=_HEADS.get(config.gpt2_name, 12),
                             gelu=gelu, tokenizer=tokenizer, ln_scale=config.ln_scale, in_weight=config.in_weight)
