@@ -14,7 +14,8 @@ dev = torch.device("cuda", 0)
 m = B200CaptionModel(synthetic.make_state_dict(a, seed=1234), dev, vit_heads=a.vit_heads, gpt_heads=a.gpt_heads, chunk_frames=1024)
 host = synthetic.make_batch_u8(0, B, T).pin_memory()
 devf = host.to(dev)
-pipe = m.pipeline(max_new_tokens=20)
+pipe = m.pipeline(max_new_tokens=20, decode_group=4)
+pipe.warm(devf)
 
 
 def clock():
@@ -29,11 +30,9 @@ def block(fn, steps):
         s_.wait_event(e0)
     for i in range(steps):
         fn()
-        if i == steps // 2:
-            c = clock()
     torch.cuda.current_stream().wait_event(pipe.last_event())
     e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / steps, c
+    return e0.elapsed_time(e1) / steps, ''
 
 
 res = lambda: pipe.submit(devf, to_host=False)

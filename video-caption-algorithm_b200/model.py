@@ -434,12 +434,18 @@ class CaptionPipeline:
         return self._last_done
 
     def warm(self, frames_u8: torch.Tensor, after_decode=None) -> None:
-        """Run every decode-group size once (1..decode_group batches of this shape) so that all CUDA graphs, KV caches and
-        workspaces the steady state will need exist before the first timed / latency-sensitive batch."""
+        """Run every decode-group size once (1..decode_group batches of this shape) and touch every pipeline slot, so that
+        all CUDA graphs, KV caches, workspaces, per-slot device frame buffers and pinned result buffers the steady state
+        will need exist before the first timed / latency-sensitive batch (a cudaMalloc or a pinned allocation inside the
+        stream of batches synchronises the device).  Pass a host tensor to warm the host-buffer path."""
+        to_host = frames_u8.device.type == "cpu"
         for g in range(1, self.group + 1):
             for _ in range(g):
-                self.submit(frames_u8, to_host=False, after_decode=after_decode)
+                self.submit(frames_u8, to_host=to_host, after_decode=after_decode)
             self.drain()
+        for _ in range(self.depth):
+            self.submit(frames_u8, to_host=to_host, after_decode=after_decode)
+        self.drain()
 
     def drain(self) -> None:
         self._flush()
