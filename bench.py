@@ -108,8 +108,10 @@ def run_reference(args):
         "impl": "reference", "metric": "captions/sec (16-frame clips)", "value": base["value"], "unit": "captions/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"ViT-B/16 + GPT-2 small, {args.frames} frames 224x224 per video, greedy {args.max_new} tokens; "
-                               "each step = 1 video on the host CPU (bounded sample of the batch-64 workload)"},
+        "config": {"workload": f"ViT-B/16 + GPT-2 small, {args.batch} videos x {args.frames} frames 224x224 per GPU, greedy {args.max_new} tokens "
+                               f"(BASELINE.json configs[1]; configs[2] layout at N>1), random-init weights",
+                   "videos_per_gpu": args.batch, "frames": args.frames, "max_new_tokens": args.max_new,
+                   "sample": "each step = 1 video of that workload on the host CPU, fp32, all host threads (bounded sample)"},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
