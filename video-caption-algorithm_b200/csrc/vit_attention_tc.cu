@@ -188,6 +188,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         const int frame = item / p.heads, head = item - frame * p.heads;
         // keys beyond the MMA's 256: raw scores q_row . k_j on the CUDA cores, before waiting for the tensor core
         float sx[AT_MAX_EXTRA];
+        uint4 vx0[8];
         if (p.extra > 0) {
           const int buf = it & 1;
           mbar_wait(&qkv_full[buf], (it >> 1) & 1);            // the Q tile of this item has landed
@@ -214,6 +215,11 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             }
             sx[e] = acc;
           }
+          // V row of the first extra key: requested now (q is dead), used in the output pass — its L2 latency hides behind
+          // the S MMA and the softmax instead of sitting between the PV MMA and the store
+          const uint4* vp0 = reinterpret_cast<const uint4*>(p.qkv + (static_cast<size_t>(frame) * p.tokens + NK) * 3 * p.D + 2 * p.D + head * 64);
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) vx0[c8] = __ldg(vp0 + c8);
         }
         mbar_wait(&s_full[t], par);
         tc_fence_after();
@@ -300,7 +306,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             const uint4* vp = reinterpret_cast<const uint4*>(p.qkv + (static_cast<size_t>(frame) * p.tokens + NK + e) * 3 * p.D + 2 * p.D + head * 64);
 #pragma unroll
             for (int c8 = 0; c8 < 8; ++c8) {
-              const uint4 u = __ldg(vp + c8);
+              const uint4 u = e == 0 ? vx0[c8] : __ldg(vp + c8);
               const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
               r[c8 * 8 + 0] = __float_as_uint(fmaf(sx[e], a.x, __uint_as_float(r[c8 * 8 + 0])));
               r[c8 * 8 + 1] = __float_as_uint(fmaf(sx[e], a.y, __uint_as_float(r[c8 * 8 + 1])));
