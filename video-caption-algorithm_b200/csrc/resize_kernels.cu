@@ -22,6 +22,7 @@ namespace {
 
 constexpr int RS_PREC = 22;
 constexpr int RS_ROWS = 8;            // input rows per CTA in the horizontal pass
+constexpr int RS_VROWS = 8;           // output rows per CTA in the vertical pass (consecutive rows share most of their taps: L1 hits)
 constexpr int RS_KREG = 8;            // taps kept in registers per output column (scale <= 3.5); longer windows re-read the table
 
 __device__ __forceinline__ uint32_t clip8(int v) {
@@ -50,8 +51,8 @@ __global__ void __launch_bounds__(256) resize_h_kernel(const uint8_t* __restrict
     for (int v = threadIdx.x; v < body; v += blockDim.x)
       *reinterpret_cast<uint4*>(s_in + in_head + 16 * v) = __ldg(reinterpret_cast<const uint4*>(gin + in_head) + v);
     const int tail0 = in_head + 16 * body;
-    for (int i = threadIdx.x; i < in_total; i += blockDim.x)
-      if (i < in_head || i >= tail0) s_in[i] = __ldg(gin + i);
+    for (int i = threadIdx.x; i < in_head && i < in_total; i += blockDim.x) s_in[i] = __ldg(gin + i);
+    for (int i = tail0 + threadIdx.x; i < in_total; i += blockDim.x) s_in[i] = __ldg(gin + i);
   }
   __syncthreads();
   // one output column per thread (its window and weights live in registers), all rows of the CTA
@@ -63,11 +64,24 @@ __global__ void __launch_bounds__(256) resize_h_kernel(const uint8_t* __restrict
 #pragma unroll
       for (int t = 0; t < RS_KREG; ++t) w[t] = t < cnt ? __ldg(k + t) : 0;
       for (int r = 0; r < n_rows; ++r) {
-        const uint8_t* p = s_in + r * in_bytes + xmin * 3;
+        // the window's 24 bytes as seven aligned 32-bit words, realigned with funnel shifts: a third of the shared-memory
+        // instructions of byte loads (bytes past the window meet zero weights; the buffer has slack behind the last row)
+        const uint32_t a = smem_u32(s_in + r * in_bytes + xmin * 3);
+        const uint32_t base = a & ~3u, sh = (a & 3u) * 8u;
+        uint32_t u[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u[j]) : "r"(base + 4 * j));
         int a0 = 1 << (RS_PREC - 1), a1 = a0, a2 = a0;
 #pragma unroll
-        for (int t = 0; t < RS_KREG; ++t)
-          if (t < cnt) { a0 += p[3 * t] * w[t]; a1 += p[3 * t + 1] * w[t]; a2 += p[3 * t + 2] * w[t]; }
+        for (int j = 0; j < 6; ++j) {
+          const uint32_t v = __funnelshift_r(u[j], u[j + 1], sh);       // bytes 4j .. 4j+3 of the window
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int i = 4 * j + b, t = i / 3, c = i - 3 * t;           // compile-time after unrolling
+            const int px = static_cast<int>((v >> (8 * b)) & 255u);
+            if (c == 0) a0 += px * w[t]; else if (c == 1) a1 += px * w[t]; else a2 += px * w[t];
+          }
+        }
         uint8_t* o = s_out + r * out_bytes + xo * 3;
         o[0] = static_cast<uint8_t>(clip8(a0)); o[1] = static_cast<uint8_t>(clip8(a1)); o[2] = static_cast<uint8_t>(clip8(a2));
       }
@@ -90,32 +104,46 @@ __global__ void __launch_bounds__(256) resize_h_kernel(const uint8_t* __restrict
     for (int v = threadIdx.x; v < body; v += blockDim.x)
       reinterpret_cast<uint4*>(gout + out_head)[v] = *reinterpret_cast<const uint4*>(s_out + out_head + 16 * v);
     const int tail0 = out_head + 16 * body;
-    for (int i = threadIdx.x; i < out_total; i += blockDim.x)
-      if (i < out_head || i >= tail0) gout[i] = s_out[i];
+    for (int i = threadIdx.x; i < out_head && i < out_total; i += blockDim.x) gout[i] = s_out[i];
+    for (int i = tail0 + threadIdx.x; i < out_total; i += blockDim.x) gout[i] = s_out[i];
   }
 }
 
-// vertical pass: src [n, H, row_bytes] -> dst [n, OH, row_bytes]; one thread per 4 consecutive bytes of an output row
-__global__ void __launch_bounds__(256) resize_v_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int n, int H, int OH, int row_words,
+// vertical pass: src [n, H, row_bytes] -> dst [n, OH, row_bytes]; grid = (ceil(row_words / 256), ceil(OH / 8), n): the output rows and
+// their taps are uniform per CTA (no index arithmetic per thread), one thread per 4 consecutive bytes, taps read as coalesced words
+__global__ void __launch_bounds__(256) resize_v_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int OH, int row_words,
                                                        const int32_t* __restrict__ kk, const int32_t* __restrict__ bounds, int ksize) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(n) * OH * row_words;
-  if (idx >= total) return;
-  const int w = static_cast<int>(idx % row_words);
-  const long long t = idx / row_words;
-  const int yo = static_cast<int>(t % OH);
-  const int f = static_cast<int>(t / OH);
-  const int ymin = __ldg(bounds + 2 * yo), cnt = __ldg(bounds + 2 * yo + 1);
-  const int32_t* k = kk + static_cast<size_t>(yo) * ksize;
-  const uint32_t* p = reinterpret_cast<const uint32_t*>(src) + (static_cast<long long>(f) * H + ymin) * row_words + w;
-  int a0 = 1 << (RS_PREC - 1), a1 = a0, a2 = a0, a3 = a0;
-  for (int i = 0; i < cnt; ++i) {
-    const uint32_t u = __ldg(p + static_cast<long long>(i) * row_words);
-    const int wgt = __ldg(k + i);
-    a0 += static_cast<int>(u & 255u) * wgt; a1 += static_cast<int>((u >> 8) & 255u) * wgt;
-    a2 += static_cast<int>((u >> 16) & 255u) * wgt; a3 += static_cast<int>(u >> 24) * wgt;
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= row_words) return;
+  const int f = blockIdx.z;
+  for (int yo = blockIdx.y * RS_VROWS; yo < OH && yo < (blockIdx.y + 1) * RS_VROWS; ++yo) {
+    const int ymin = __ldg(bounds + 2 * yo), cnt = __ldg(bounds + 2 * yo + 1);
+    const int32_t* k = kk + static_cast<size_t>(yo) * ksize;
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(src) + (static_cast<long long>(f) * H + ymin) * row_words + w;
+    int a0 = 1 << (RS_PREC - 1), a1 = a0, a2 = a0, a3 = a0;
+    if (cnt <= RS_KREG) {
+      uint32_t u[RS_KREG];
+      int wt[RS_KREG];
+#pragma unroll
+      for (int i = 0; i < RS_KREG; ++i) {                  // every tap row requested before the first one is used
+        wt[i] = i < cnt ? __ldg(k + i) : 0;
+        u[i] = i < cnt ? __ldg(p + static_cast<long long>(i) * row_words) : 0u;
+      }
+#pragma unroll
+      for (int i = 0; i < RS_KREG; ++i) {
+        a0 += static_cast<int>(u[i] & 255u) * wt[i]; a1 += static_cast<int>((u[i] >> 8) & 255u) * wt[i];
+        a2 += static_cast<int>((u[i] >> 16) & 255u) * wt[i]; a3 += static_cast<int>(u[i] >> 24) * wt[i];
+      }
+    } else {
+      for (int i = 0; i < cnt; ++i) {
+        const uint32_t u = __ldg(p + static_cast<long long>(i) * row_words);
+        const int wgt = __ldg(k + i);
+        a0 += static_cast<int>(u & 255u) * wgt; a1 += static_cast<int>((u >> 8) & 255u) * wgt;
+        a2 += static_cast<int>((u >> 16) & 255u) * wgt; a3 += static_cast<int>(u >> 24) * wgt;
+      }
+    }
+    reinterpret_cast<uint32_t*>(dst)[(static_cast<long long>(f) * OH + yo) * row_words + w] = clip8(a0) | (clip8(a1) << 8) | (clip8(a2) << 16) | (clip8(a3) << 24);
   }
-  reinterpret_cast<uint32_t*>(dst)[idx] = clip8(a0) | (clip8(a1) << 8) | (clip8(a2) << 16) | (clip8(a3) << 24);
 }
 
 }  // namespace
@@ -146,9 +174,10 @@ int resize_bilinear_u8(const uint8_t* src, int n, int H, int W, uint8_t* tmp, ui
   }
   if (vH != OH) {
     const int row_words = OW * 3 / 4;
-    const long long total = static_cast<long long>(n) * OH * row_words;
+    VC_REQUIRE(OH <= 65535 && n <= 65535, "resize: grid limits (OH=%d, n=%d)", OH, n);
+    const int bt = row_words < 256 ? ((row_words + 31) / 32) * 32 : 256;
     VC_LAUNCH("resize_v", static_cast<double>(n) * (vH + OH) * OW * 3.0, s,
-              (resize_v_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(vsrc, dst, n, vH, OH, row_words, ky, by, ksize_y)));
+              (resize_v_kernel<<<dim3((row_words + bt - 1) / bt, (OH + RS_VROWS - 1) / RS_VROWS, n), bt, 0, s>>>(vsrc, dst, vH, OH, row_words, ky, by, ksize_y)));
     VC_CUDA_OK(cudaGetLastError());
   } else if (W == OW && dst != src) {
     VC_CUDA_OK(cudaMemcpyAsync(dst, src, static_cast<size_t>(n) * H * W * 3, cudaMemcpyDeviceToDevice, s));
