@@ -514,17 +514,43 @@ __global__ void __launch_bounds__(128) vit_cls_attention_kernel(const __nv_bfloa
   }
   sum = warp_sum(sum);
   __syncwarp();
-  float o0 = 0.f, o1 = 0.f;
-#pragma unroll 8
-  for (int j = 0; j < tokens; ++j) {
-    const float2 v = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(base + static_cast<long long>(j) * 3 * D + 2 * D) + lane));
-    const float pj = s_p[warp][j];
-    o0 = fmaf(pj, v.x, o0);
-    o1 = fmaf(pj, v.y, o1);
+  // weighted V sum: lane = (key group kg = lane >> 3, 16-byte chunk c = lane & 7): a warp instruction covers four whole V rows
+  // (16-byte loads, 16 of them in flight per lane), each lane accumulates its 8 head dims over keys kg, kg+4, ...; the four
+  // key groups are folded with two shuffles at the end
+  float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int kg = lane >> 3, c8 = lane & 7;
+  const __nv_bfloat16* vbase = base + 2 * D + c8 * 8;
+  for (int j0 = 0; j0 < tokens; j0 += 64) {
+    uint4 u[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int j = j0 + 4 * i + kg;
+      if (j < tokens) u[i] = __ldg(reinterpret_cast<const uint4*>(vbase + static_cast<long long>(j) * 3 * D));
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int j = j0 + 4 * i + kg;
+      if (j < tokens) {
+        const float pj = s_p[warp][j];
+        const float2 a = unpack_bf16(u[i].x), b = unpack_bf16(u[i].y), cc = unpack_bf16(u[i].z), d = unpack_bf16(u[i].w);
+        o[0] = fmaf(pj, a.x, o[0]); o[1] = fmaf(pj, a.y, o[1]); o[2] = fmaf(pj, b.x, o[2]); o[3] = fmaf(pj, b.y, o[3]);
+        o[4] = fmaf(pj, cc.x, o[4]); o[5] = fmaf(pj, cc.y, o[5]); o[6] = fmaf(pj, d.x, o[6]); o[7] = fmaf(pj, d.y, o[7]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 8);
+    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
   }
   const float inv = 1.f / sum;
   const long long orow = compact ? fr : static_cast<long long>(frame) * tokens + qrow;
-  *(reinterpret_cast<uint32_t*>(out + orow * D + head * HD) + lane) = pack_bf16(o0 * inv, o1 * inv);
+  if (kg == 0) {
+    uint4 w;
+    w.x = pack_bf16(o[0] * inv, o[1] * inv); w.y = pack_bf16(o[2] * inv, o[3] * inv);
+    w.z = pack_bf16(o[4] * inv, o[5] * inv); w.w = pack_bf16(o[6] * inv, o[7] * inv);
+    *(reinterpret_cast<uint4*>(out + orow * D + head * HD) + c8) = w;
+  }
 }
 
 int vit_row_attention(const void* qkv, void* out, int n_frames, int tokens, int heads, int row0, int n_rows, cudaStream_t s) {
