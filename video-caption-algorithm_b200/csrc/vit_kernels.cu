@@ -580,7 +580,7 @@ int vit_cls_attention(const void* qkv, void* out, int n_frames, int tokens, int 
 // One CTA per video: class-token temporal mean (video_encoder.py:256-258) -> encoder.proj
 // Linear(dim, video_dim) (:316) -> F.layer_norm(no affine) * ln_scale, * in_weight
 // (core/engine.py:45-50) -> decoder.mapper Linear(video_dim, P*H) (text_decoder.py:36-45,69).
-__global__ void __launch_bounds__(256) pool_prefix_kernel(const float* __restrict__ cls, int T, int dim,
+__global__ void __launch_bounds__(1024) pool_prefix_kernel(const float* __restrict__ cls, int T, int dim,
                                                           const float* __restrict__ head_w, const float* __restrict__ head_b,
                                                           int video_dim, float ln_scale, float in_weight,
                                                           const float* __restrict__ mapper_w, const float* __restrict__ mapper_b,
@@ -592,19 +592,29 @@ __global__ void __launch_bounds__(256) pool_prefix_kernel(const float* __restric
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
   for (int c = tid; c < dim; c += blockDim.x) {
     float acc = 0.f;
-    for (int t = 0; t < T; ++t) acc += cls[(static_cast<long long>(b) * T + t) * dim + c];
+#pragma unroll 8
+    for (int t = 0; t < T; ++t) acc += cls[(static_cast<long long>(b) * T + t) * dim + c];     // same order, loads batched
     s_pool[c] = acc / static_cast<float>(T);
   }
   __syncthreads();
-  for (int o = warp; o < video_dim; o += nwarp) {
-    const float* w = head_w + static_cast<long long>(o) * dim;
-    float acc = 0.f;
-    for (int c = lane; c < dim; c += 32) acc = fmaf(s_pool[c], __ldg(w + c), acc);
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      const float f = acc + head_b[o];
-      s_feat[o] = f;
-      feat_out[static_cast<long long>(b) * video_dim + o] = f;
+  // four output rows per warp iteration: their weight loads are independent, so one memory round trip serves four outputs
+  // (each output keeps its own lane-strided accumulation order)
+  for (int o0 = warp * 4; o0 < video_dim; o0 += nwarp * 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = lane; c < dim; c += 32) {
+      const float x = s_pool[c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (o0 + i < video_dim) acc[i] = fmaf(x, __ldg(head_w + static_cast<long long>(o0 + i) * dim + c), acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float a = warp_sum(acc[i]);
+      if (lane == 0 && o0 + i < video_dim) {
+        const float f = a + head_b[o0 + i];
+        s_feat[o0 + i] = f;
+        feat_out[static_cast<long long>(b) * video_dim + o0 + i] = f;
+      }
     }
   }
   __syncthreads();
@@ -626,12 +636,19 @@ __global__ void __launch_bounds__(256) pool_prefix_kernel(const float* __restric
     s_pool[c] = e;   // reuse as emb (video_dim <= dim)
   }
   __syncthreads();
-  for (int o = warp; o < mapper_out; o += nwarp) {
-    const float* w = mapper_w + static_cast<long long>(o) * video_dim;
-    float acc = 0.f;
-    for (int c = lane; c < video_dim; c += 32) acc = fmaf(s_pool[c], __ldg(w + c), acc);
-    acc = warp_sum(acc);
-    if (lane == 0) prefix_out[static_cast<long long>(b) * mapper_out + o] = acc + mapper_b[o];
+  for (int o0 = warp * 4; o0 < mapper_out; o0 += nwarp * 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = lane; c < video_dim; c += 32) {
+      const float x = s_pool[c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (o0 + i < mapper_out) acc[i] = fmaf(x, __ldg(mapper_w + static_cast<long long>(o0 + i) * video_dim + c), acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float a = warp_sum(acc[i]);
+      if (lane == 0 && o0 + i < mapper_out) prefix_out[static_cast<long long>(b) * mapper_out + o0 + i] = a + mapper_b[o0 + i];
+    }
   }
 }
 
@@ -642,7 +659,7 @@ int pool_prefix(const float* cls, int B, int T, int dim, const float* head_w, co
   if (B <= 0) return 0;
   const int smem = (dim + video_dim) * sizeof(float);
   VC_LAUNCH("pool_prefix", static_cast<double>(B) * (T * dim + (dim + mapper_out) * video_dim) * 4.0, s,
-            (pool_prefix_kernel<<<B, 256, smem, s>>>(cls, T, dim, head_w, head_b, video_dim, ln_scale, in_weight, mapper_w,
+            (pool_prefix_kernel<<<B, 1024, smem, s>>>(cls, T, dim, head_w, head_b, video_dim, ln_scale, in_weight, mapper_w,
                                                      mapper_b, mapper_out, feat_out, prefix_out)));
   VC_CUDA_OK(cudaGetLastError());
   return 0;
