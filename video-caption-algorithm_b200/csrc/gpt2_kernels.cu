@@ -277,7 +277,9 @@ int gpt_attention(const void* qkv, const float* P, int ksplit, const float* bias
       attr = ATT_SMEM_MAX_S * (2 * ATT_ROW_B + GHD * 4);
     }
     VC_LAUNCH("gpt_attention", bytes, s,
-              VC_CUDA_OK(launch_pdl(gpt_attention_smem_kernel, dim3(n_seq * c->heads), dim3(128), static_cast<size_t>(smem), s,
+              // one new position per sequence: only one warp computes, so the CTA is that one warp (32 CTAs per SM instead of
+              // 16, no idle threads): n_seq * heads CTAs of a 256-sequence step stay in a single wave (19.4 -> 16.6 ms per 20 tokens)
+              VC_CUDA_OK(launch_pdl(gpt_attention_smem_kernel, dim3(n_seq * c->heads), dim3(L == 1 ? 32 : 128), static_cast<size_t>(smem), s,
                                     static_cast<const __nv_bfloat16*>(qkv), P, ksplit, bias, static_cast<__nv_bfloat16*>(out),
                                     static_cast<__nv_bfloat16*>(c->kv), static_cast<const int32_t*>(c->slot), layer, c->n_seq, n_seq * L, c->heads,
                                     c->s_max, L, past_len)));
