@@ -33,6 +33,7 @@ constexpr int SK_WARPS = 4;             // 4 warps x 16 features = 64 features p
 constexpr int SK_BN = SK_WARPS * 16;
 constexpr int SK_MT = 64;               // sequences per CTA pass (8 n-tiles of 8)
 constexpr int SK_KB = 64;               // k elements per register batch (2 MMA pairs)
+constexpr int SK_STAGE_MAX = 384;       // widest K slice whose [64 x slice] activation block is staged in shared memory (53 KB)
 
 // Weights are streamed once per step: keep them out of L1 and mark them first-to-evict in L2, so that 247 MB of decoder
 // weights per step do not push the concurrently running encoder's working set out of the 126 MB L2 (CaptionPipeline).
@@ -316,7 +317,8 @@ __global__ void __launch_bounds__(256) bias_act_kernel(const float* __restrict__
 
 // K-slices of a multiple of 64; aim for >= ~200 CTAs (row tiles included) without exploding the partial buffer: the fp32
 // partials are written and read back through L2 once per slice, which is the dominant traffic of a step beyond 64 rows.
-// Slices stay <= 256 wide where possible so that the activation block is staged in shared memory.
+// Slices stay <= 384 wide where possible so that the activation block is staged in shared memory; at four row tiles this
+// keeps every product of GPT-2 small within one wave of CTAs (384-432 CTAs at three per SM).
 int skinny_ksplit(int N, int K, int row_tiles) {
   const int blocks = (N / SK_BN) * (row_tiles > 0 ? row_tiles : 1);
   const int kb = K / SK_KB;
@@ -325,7 +327,7 @@ int skinny_ksplit(int N, int K, int row_tiles) {
   for (int ks = 1; ks <= kb; ++ks) {
     if (kb % ks) continue;
     best = ks;
-    if (blocks * ks >= 200 && K / ks <= 4 * SK_KB) break;
+    if (blocks * ks >= 200 && K / ks <= SK_STAGE_MAX) break;
   }
   return best;
 }
@@ -336,8 +338,13 @@ int skinny_gemm(const void* x, const void* W, float* P, int M, int N, int K, int
   VC_REQUIRE(ksplit >= 1 && (K / SK_KB) % ksplit == 0, "skinny_gemm: ksplit=%d does not divide K/64=%d", ksplit, K / SK_KB);
   dim3 grid(N / SK_BN, ksplit, (M + SK_MT - 1) / SK_MT);
   const int kslice = K / ksplit;
-  if (kslice <= 256) {
+  if (kslice <= SK_STAGE_MAX) {
     const size_t smem = static_cast<size_t>(SK_MT) * (kslice * 2 + 64);
+    static bool attr = false;
+    if (!attr) {
+      VC_CUDA_OK(cudaFuncSetAttribute(skinny_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_MT * (SK_STAGE_MAX * 2 + 64)));
+      attr = true;
+    }
     VC_LAUNCH("skinny_gemm", static_cast<double>(N) * K * 2.0, s,
               VC_CUDA_OK(launch_pdl(skinny_gemm_kernel<true>, grid, dim3(SK_WARPS * 32), smem, s, static_cast<const __nv_bfloat16*>(x),
                                     static_cast<const __nv_bfloat16*>(W), P, M, N, K, kslice)));

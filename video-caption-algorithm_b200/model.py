@@ -339,7 +339,7 @@ class CaptionPipeline:
 
     def __init__(self, model: B200CaptionModel, max_new_tokens: int, decode_group: int = 2, overlap_decode: bool = True):
         """decode_group: consecutive batches whose sequences are decoded together (group * batch <= 256).  The decode
-        chain is mostly latency-bound: 20 tokens cost 9.6 ms for 64 sequences and 16.6 ms for 256, so
+        chain is mostly latency-bound: 20 tokens cost 9.6 ms for 64 sequences, 11.8 ms for 128 and 15.7 ms for 256, so
         decoding several encoder batches per chain cuts the decode cost per batch.  Per-sequence results do not depend
         on the grouping.  overlap_decode=False runs the chain on the encoder's stream (no concurrency)."""
         self.m = model
