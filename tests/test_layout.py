@@ -83,3 +83,18 @@ def test_checkpoint_reader_unwraps_model_state(tmp_path):
     torch.save({"epoch": 3}, tmp_path / "bad.pt")
     with pytest.raises(ValueError):
         read_checkpoint(tmp_path / "bad.pt")
+
+
+def test_resize_coefficient_tables_match_oracle_rule():
+    """The product's host-side Pillow coefficient tables (resample.py) against the oracle's independent restatement, for
+    shrinking, growing and identity sizes: same windows, same 22-bit weights."""
+    from vcb200.resample import pillow_bilinear_coeffs
+    from oracle import vc_oracle as O
+    for in_size, out_size in [(480, 224), (360, 224), (1280, 224), (100, 224), (224, 224), (225, 224), (37, 224)]:
+        kk, bounds, ks = pillow_bilinear_coeffs(in_size, out_size)
+        wts, bnd = O.pillow_bilinear_coeffs(in_size, out_size)
+        assert kk.shape == (out_size, ks) and len(wts) == out_size
+        for i in range(out_size):
+            assert tuple(bounds[i]) == tuple(bnd[i])
+            assert kk[i].tolist() == wts[i]
+            assert abs(int(kk[i].sum()) - (1 << 22)) <= ks          # normalised weights sum to 1.0 in 22-bit fixed point
