@@ -288,8 +288,12 @@ static int gpt_step_skinny(const VcGptWeights* w, const float* embeds, int n_seq
   // activation block every CTA then pulls through L1 costs.
   const bool fused_fc = H % 256 == 0 && getenv("VC_DECODE_FUSED_FC") != nullptr;
   int e;
-  if ((e = gpt_add_pos(embeds, w->wpe, b.h, n_seq, L, past_len, H, s))) return e;
-  if ((e = layernorm_f32_bf16(b.h, w->layer[0].ln1_g, w->layer[0].ln1_b, b.xn, M, H, 1e-5f, s))) return e;
+  if (H % 128 == 0 && H <= 1024) {
+    if ((e = gpt_add_pos_ln(embeds, w->wpe, b.h, b.xn, w->layer[0].ln1_g, w->layer[0].ln1_b, n_seq, L, past_len, H, 1e-5f, s))) return e;
+  } else {
+    if ((e = gpt_add_pos(embeds, w->wpe, b.h, n_seq, L, past_len, H, s))) return e;
+    if ((e = layernorm_f32_bf16(b.h, w->layer[0].ln1_g, w->layer[0].ln1_b, b.xn, M, H, 1e-5f, s))) return e;
+  }
   for (int l = 0; l < w->layers; ++l) {
     const VcGptLayer& Ly = w->layer[l];
     if ((e = skinny_gemm(b.xn, Ly.attn_w, b.partial, M, 3 * H, H, ks_attn, s))) return e;

@@ -41,6 +41,66 @@ int gpt_add_pos(const float* embeds, const float* wpe, float* h, int n_seq, int 
   return 0;
 }
 
+// h = embeds + wpe[pos]; xn = LayerNorm(h) (bf16): the first two ops of a forward in one kernel, one warp per row
+// (dim <= 1024, dim % 128 == 0), so a decode step starts with one dependent launch instead of two.
+__global__ void __launch_bounds__(256) add_pos_ln_kernel(const float* __restrict__ e, const float* __restrict__ wpe, float* __restrict__ h,
+                                                         __nv_bfloat16* __restrict__ xn, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, int rows, int L, int past_len, int dim, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  const int nv = dim >> 7;                               // float4 per lane
+  float4 g[8], bt[8], pe[8];
+  const int l = row < rows ? row % L : 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < nv) {                                        // constants: before the wait
+      g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+      bt[i] = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+      pe[i] = __ldg(reinterpret_cast<const float4*>(wpe + static_cast<long long>(past_len + l) * dim) + lane + 32 * i);
+    }
+  pdl_wait();
+  pdl_launch_dependents();
+  if (row >= rows) return;
+  float4 v[8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < nv) {
+      const float4 a = reinterpret_cast<const float4*>(e + static_cast<long long>(row) * dim)[lane + 32 * i];
+      v[i] = make_float4(a.x + pe[i].x, a.y + pe[i].y, a.z + pe[i].z, a.w + pe[i].w);
+      reinterpret_cast<float4*>(h + static_cast<long long>(row) * dim)[lane + 32 * i] = v[i];
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  const float mean = warp_sum(sum) / static_cast<float>(dim);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(dim) + eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < nv) {
+      uint2 w;
+      w.x = pack_bf16((v[i].x - mean) * rstd * g[i].x + bt[i].x, (v[i].y - mean) * rstd * g[i].y + bt[i].y);
+      w.y = pack_bf16((v[i].z - mean) * rstd * g[i].z + bt[i].z, (v[i].w - mean) * rstd * g[i].w + bt[i].w);
+      reinterpret_cast<uint2*>(xn + static_cast<long long>(row) * dim)[lane + 32 * i] = w;
+    }
+}
+int gpt_add_pos_ln(const float* embeds, const float* wpe, float* h, void* xn, const float* gamma, const float* beta, int n_seq, int L,
+                   int past_len, int dim, float eps, cudaStream_t s) {
+  VC_REQUIRE(dim % 128 == 0 && dim <= 1024, "add_pos_ln: dim=%d", dim);
+  const int rows = n_seq * L;
+  if (rows == 0) return 0;
+  VC_LAUNCH("gpt_add_pos_ln", rows * dim * 10.0, s,
+            VC_CUDA_OK(launch_pdl(add_pos_ln_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, embeds, wpe, h, static_cast<__nv_bfloat16*>(xn), gamma, beta,
+                                  rows, L, past_len, dim, eps)));
+  VC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------ KV-cache attention
 // cache layout: kv[layer][k|v][seq][head][s_max][64] bf16.  slot[seq][pos] (optional) is the
 // physical seq row that holds position pos of logical row seq (beam search indirection).

@@ -70,6 +70,9 @@ int linear_bias_f32(const float* x, const float* w, const float* b, float* y, in
 
 // gpt2_kernels.cu
 int gpt_add_pos(const float* embeds, const float* wpe, float* h, int n_seq, int L, int past_len, int dim, cudaStream_t s);
+// h = embeds + wpe[past_len + l]; xn = LayerNorm(h) as bf16 — one kernel
+int gpt_add_pos_ln(const float* embeds, const float* wpe, float* h, void* xn_bf16, const float* gamma, const float* beta, int n_seq, int L,
+                   int past_len, int dim, float eps, cudaStream_t s);
 // qkv: bf16 [rows, 3H] (prefill) or, when P != null, fp32 split-K partials [ksplit][rows][3H] + bias (decode step)
 int gpt_attention(const void* qkv, const float* P, int ksplit, const float* bias, void* out, const VcKvCache* cache, int layer,
                   int n_seq, int L, int past_len, cudaStream_t s);
