@@ -69,6 +69,10 @@ typedef struct {
   const float* ln2_g; const float* ln2_b;
   const void* fc_w;    const float* fc_b;    /* bf16 [4H, H] */
   const void* mproj_w; const float* mproj_b; /* bf16 [H, 4H] */
+  /* LayerNorm folded into the consumer product (decode chain): W' = bf16(gamma (.) W) [out, H], cs[n] = sum_k W'[n][k],
+   * bf[n] = b[n] + sum_k beta[k] W[n][k]  so that  LN(h) W^T + b = rstd (h W'^T - mean cs) + bf.  NULL = not packed. */
+  const void* attn_wf; const float* attn_cs; const float* attn_bf;   /* ln_1 into c_attn */
+  const void* fc_wf;   const float* fc_cs;   const float* fc_bf;     /* ln_2 into c_fc   */
 } VcGptLayer;
 
 typedef struct {
@@ -76,6 +80,8 @@ typedef struct {
   const void* wte;            /* bf16 [vocab_pad, H] (tied lm_head) */
   const float* wpe;           /* fp32 [n_pos, H] */
   const float* lnf_g; const float* lnf_b;
+  const void* lmh_w;          /* bf16 [vocab_pad, H] = bf16(ln_f.gamma (.) wte): ln_f folded into the tied lm_head (NULL = not packed) */
+  const float* lmh_cs; const float* lmh_b;   /* fp32 [vocab_pad]: column sums of lmh_w, wte . ln_f.beta */
   const VcGptLayer* layer;    /* host array [layers] */
 } VcGptWeights;
 
@@ -92,6 +98,10 @@ int vc_abi_version(void);
 int vc_num_sms(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 long long vc_launch_count(void);
+/* optional in-kernel timeline of the decode chain (tools/trace_decode.py): device buffer of 8 + 8*max_records uint64, buf[0] = record
+ * counter (zero it first); every record = {kernel id | cta << 8, %globaltimer at entry, after the dependency wait, after the
+ * activations arrived, after the MMAs, after the reduction barrier, -, at exit}.  NULL switches it off. */
+int vc_debug_trace(void* buf_u64, int max_records);
 /* optional per-kernel CUDA-event timing on the launch stream (bench.py roofline pass) */
 int vc_prof_begin(void);
 int vc_prof_end(int max_rows, char* names /*[max_rows][48]*/, float* total_ms, int* calls, double* work);

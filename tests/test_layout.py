@@ -23,7 +23,7 @@ def test_header_symbols_are_exported():
     missing = [s for s in sorted(declared) if not hasattr(dll, s)]
     assert not missing, missing
     assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
-    assert dll.vc_abi_version() == 1
+    assert dll.vc_abi_version() == L.ABI_VERSION
 
 
 def test_product_never_imports_oracle():
@@ -98,3 +98,27 @@ def test_resize_coefficient_tables_match_oracle_rule():
             assert tuple(bounds[i]) == tuple(bnd[i])
             assert kk[i].tolist() == wts[i]
             assert abs(int(kk[i].sum()) - (1 << 22)) <= ks          # normalised weights sum to 1.0 in 22-bit fixed point
+
+
+def test_layernorm_folding_identity():
+    """packing.fold_layernorm: LN(x) W^T + b == rstd * (x W'^T - mean * cs) + b' (what the decode chain and the encoder's
+    folded GEMM epilogues compute), checked in fp64 against the unfused form on the bf16-rounded folded weights."""
+    from vcb200.packing import fold_layernorm
+    g = torch.Generator().manual_seed(0)
+    H, N, M = 768, 96, 7
+    x = torch.randn(M, H, generator=g).double() * 3 + 0.7
+    w = torch.randn(N, H, generator=g) * 0.05
+    b = torch.randn(N, generator=g) * 0.1
+    gamma = 1 + 0.2 * torch.randn(H, generator=g)
+    beta = 0.1 * torch.randn(H, generator=g)
+    wf, cs, b2 = fold_layernorm(w, b, gamma, beta)
+    assert wf.dtype == torch.bfloat16 and cs.dtype == torch.float32 and b2.dtype == torch.float32
+    mean = x.mean(1, keepdim=True)
+    rstd = 1.0 / torch.sqrt(x.var(1, unbiased=False, keepdim=True) + 1e-5)
+    folded = rstd * (x @ wf.double().t() - mean * cs.double()) + b2.double()
+    # unfused with the same rounded weights: gamma (.) W -> wf, beta W^T exact
+    ref = ((x - mean) * rstd) @ wf.double().t() + (w.double() @ beta.double() + b.double())
+    assert (folded - ref).abs().max().item() < 1e-4          # fp32 storage of cs / b'
+    # and against the textbook form with unrounded weights: only the bf16 rounding of W' separates them
+    full = torch.nn.functional.layer_norm(x, (H,), gamma.double(), beta.double(), 1e-5) @ w.double().t() + b.double()
+    assert (folded - full).abs().max().item() < 0.05

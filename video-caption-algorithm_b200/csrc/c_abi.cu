@@ -79,7 +79,7 @@ static VitBuffers carve_vit(const VcVitWeights* w, int chunk_frames, void* base)
 
 struct GptBuffers {
   float* h; void* xn; void* qkv; void* att; void* hid; float* emb; float* logits; int32_t* finished; int32_t* next; float* partial;
-  float* cand_v; int* cand_i; unsigned int* bar;
+  float* stat; float* cand_v; int* cand_i;
   size_t total;
 };
 constexpr int kDecodeMaxRows = 1024;  // n_seq * new positions handled by the weight-streaming kernels; beyond: tcgen05 GEMM path
@@ -98,21 +98,28 @@ static GptBuffers carve_gpt(const VcGptWeights* w, int n_seq, int max_rows, void
   b.finished = reinterpret_cast<int32_t*>(p + off); off += align_up(static_cast<size_t>(n_seq) * 4, 1024);
   b.next = reinterpret_cast<int32_t*>(p + off);     off += align_up(static_cast<size_t>(n_seq) * 4, 1024);
   {
-    // fp32 split-K partials of the decode step's GEMMs (widest product), per-CTA argmax candidates, grid barrier
+    // fp32 split-K partials of the fallback chain's GEMMs (widest product); partial LayerNorm statistics [16][rows] and the
+    // lm_head's per-CTA argmax candidates [n_seq][ctas] of the decode chain
     const size_t rows = R < static_cast<size_t>(kDecodeMaxRows) ? R : static_cast<size_t>(kDecodeMaxRows);
     const int H = w->dim;
-    size_t m = std::max(decode_partial_floats_per_row(w), decode_lean_partial_floats_per_row(w));
-    m = std::max(m, static_cast<size_t>(skinny_ksplit(3 * H, H)) * 3 * H);
+    size_t m = static_cast<size_t>(skinny_ksplit(3 * H, H)) * 3 * H;
     m = std::max(m, static_cast<size_t>(skinny_ksplit(H, H)) * H);
     m = std::max(m, static_cast<size_t>(skinny_ksplit(4 * H, H)) * 4 * H);
     m = std::max(m, static_cast<size_t>(skinny_ksplit(H, 4 * H)) * H);
     b.partial = reinterpret_cast<float*>(p + off);  off += align_up(m * rows * 4, 1024);
-    b.cand_v = reinterpret_cast<float*>(p + off);   off += align_up(static_cast<size_t>(256) * 128 * 4, 1024);
-    b.cand_i = reinterpret_cast<int*>(p + off);     off += align_up(static_cast<size_t>(256) * 128 * 4, 1024);
-    b.bar = reinterpret_cast<unsigned int*>(p + off); off += 1024;
+    b.stat = reinterpret_cast<float*>(p + off);     off += align_up(static_cast<size_t>(16) * rows * 8, 1024);
+    const size_t nc = static_cast<size_t>(n_seq) * 256;
+    b.cand_v = reinterpret_cast<float*>(p + off);   off += align_up(nc * 4, 1024);
+    b.cand_i = reinterpret_cast<int*>(p + off);     off += align_up(nc * 4, 1024);
   }
   b.total = off;
   return b;
+}
+static ChainBuffers chain_buffers(const GptBuffers& b) { return ChainBuffers{b.h, b.xn, b.qkv, b.att, b.hid, b.stat, b.cand_v, b.cand_i}; }
+// VC_DECODE_CHAIN=1 (A/B switch): the round-1 split-K kernel chain instead of decode_chain.cu
+static bool use_chain_v2(const VcGptWeights* w, int rows) {
+  static const bool v1 = getenv("VC_DECODE_CHAIN") != nullptr && atoi(getenv("VC_DECODE_CHAIN")) == 1;
+  return !v1 && chain_supported(w, rows) && chain_lmhead_ctas() <= 256;
 }
 
 }  // namespace vc
@@ -122,7 +129,7 @@ using namespace vc;
 extern "C" {
 
 const char* vc_last_error(void) { return g_err; }
-int vc_abi_version(void) { return 1; }
+int vc_abi_version(void) { return 2; }
 int vc_num_sms(void) {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
@@ -130,6 +137,7 @@ int vc_num_sms(void) {
   return n;
 }
 long long vc_launch_count(void) { return g_launches.load(); }
+int vc_debug_trace(void* buf_u64, int max_records) { return chain_set_trace(buf_u64, max_records); }
 
 int vc_prof_begin(void) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -318,31 +326,15 @@ static int gpt_step_skinny(const VcGptWeights* w, const float* embeds, int n_seq
   return skinny_gemm(b.xn, w->wte, logits_out, n_seq, w->vocab_pad, H, 1, s);
 }
 
-// VC_DECODE_PERSISTENT=1 selects the single-launch cooperative decode kernel (decode_step.cu); measured on B200 it is
-// device-barrier bound (~86 barriers x ~4.5 us per step) and not yet faster than the PDL kernel chain, which is the default.
-// VC_DECODE_PERSISTENT=2 selects the lean persistent kernel (decode_lean.cu: symmetric warps, mma.sync, n_seq <= 64).
-static int persistent_decode_mode() {
-  static const int mode = getenv("VC_DECODE_PERSISTENT") != nullptr ? atoi(getenv("VC_DECODE_PERSISTENT")) : 0;
-  return mode;
-}
-static bool use_persistent_decode() { return persistent_decode_mode() == 1; }
-static bool use_lean_decode(const VcGptWeights* w, int n_seq, const VcKvCache* cache) {
-  return persistent_decode_mode() == 2 && decode_lean_supported(w, n_seq, cache);
-}
-
-static DecodeBuffers decode_buffers(const GptBuffers& b) {
-  return DecodeBuffers{b.h, b.xn, b.att, b.hid, b.partial, b.cand_v, b.cand_i, b.bar};
-}
-
 static int gpt_forward_impl(const VcGptWeights* w, const float* embeds, int n_seq, int L, int past_len, VcKvCache* cache,
                             const GptBuffers& b, float* logits_out, cudaStream_t s) {
   const int H = w->dim, M = n_seq * L;
   int e;
-  // one new position per sequence
-  if (L == 1 && past_len >= 1 && use_lean_decode(w, n_seq, cache))
-    return decode_lean_steps(w, decode_buffers(b), b.logits, cache, n_seq, past_len, 1, embeds, nullptr, logits_out, 0, s);
-  if (L == 1 && past_len >= 1 && use_persistent_decode() && decode_supported(w, n_seq, cache))
-    return decode_steps(w, decode_buffers(b), cache, n_seq, past_len, 1, embeds, nullptr, logits_out, 0, s);
+  if (use_chain_v2(w, M)) {
+    const ChainBuffers cb = chain_buffers(b);
+    if ((e = chain_add_pos_stats(w, embeds, cb, n_seq, L, past_len, s))) return e;
+    return chain_layers(w, cb, n_seq, L, past_len, cache, logits_out, w->vocab_pad, s);
+  }
   // VC_PREFILL_TCGEN05=1 (A/B switch, read per call): multi-position forwards take the tcgen05 GEMM path as before
   const bool chain_ok = L == 1 ? n_seq <= 256 || getenv("VC_PREFILL_TCGEN05") == nullptr : getenv("VC_PREFILL_TCGEN05") == nullptr;
   if (chain_ok && M <= kDecodeMaxRows && w->vocab_pad % 64 == 0) return gpt_step_skinny(w, embeds, n_seq, L, past_len, cache, b, logits_out, s);
@@ -370,6 +362,13 @@ int vc_gpt2_forward(const VcGptWeights* w, const float* embeds, int n_seq, int L
   VC_REQUIRE(past_len + L <= w->n_pos, "gpt2_forward: position %d exceeds n_positions=%d", past_len + L, w->n_pos);
   GptBuffers b = carve_gpt(w, n_seq, n_seq * L, workspace);
   VC_REQUIRE(workspace != nullptr && workspace_bytes >= b.total, "gpt2_forward: workspace %zu < %zu bytes", workspace_bytes, b.total);
+  if (use_chain_v2(w, n_seq * L)) {
+    // logits are materialised only when the caller asks for them; next_ids come from the lm_head's per-CTA candidates
+    int e = gpt_forward_impl(w, embeds, n_seq, L, past_len, cache, b, logits_out, S(stream));
+    if (e) return e;
+    if (next_ids) return chain_argmax(chain_buffers(b), n_seq, next_ids, S(stream));
+    return 0;
+  }
   float* lg = logits_out ? logits_out : b.logits;
   int e = gpt_forward_impl(w, embeds, n_seq, L, past_len, cache, b, lg, S(stream));
   if (e) return e;
@@ -394,27 +393,30 @@ int vc_greedy_decode(const VcGptWeights* w, const float* prefix, int n_seq, int 
   int e;
   if ((e = greedy_init(ids_out, len_out, b.finished, n_seq, max_new, eos, s))) return e;
   if ((e = build_prefill_embeds(prefix, w->wte, prompt_ids, n_seq, P, Lp, w->dim, b.emb, s))) return e;
-  const bool fused = max_new > 1 && use_persistent_decode() && decode_supported(w, n_seq, cache);
+  // Per forward the faster of the two few-row chains is taken (decode_chain.cu up to 64 rows, the split-K chain beyond: the
+  // prefill of 64 captions is 320 rows).  decode_chain.cu's selection kernel writes the next step's input rows itself
+  // (wte[token] + wpe, bf16 copy, row statistics); after any other forward they are built from b.emb.
+  const ChainBuffers cb = chain_buffers(b);
+  bool rows_ready = false;
   for (int step = 0; step < max_new; ++step) {
     const int L = step == 0 ? L0 : 1;
     const int past = step == 0 ? 0 : L0 + step - 1;
-    float* lg = step_logits ? step_logits + static_cast<size_t>(step) * n_seq * w->vocab_pad : b.logits;
-    if (step == 1 && max_new > 1 && use_lean_decode(w, n_seq, cache)) {
-      DecodeGreedy g{1, max_new, eos, b.finished, ids_out, len_out, forced_ids, b.next};
-      return decode_lean_steps(w, decode_buffers(b), b.logits, cache, n_seq, past, max_new - 1, b.emb, &g, step_logits ? lg : nullptr,
-                               static_cast<long long>(n_seq) * w->vocab_pad, s);
-    }
-    if (step == 1 && fused) {
-      // steps 1..max_new-1 (argmax, bookkeeping and token feedback included) in ONE persistent launch
-      DecodeGreedy g{1, max_new, eos, b.finished, ids_out, len_out, forced_ids, b.next};
-      return decode_steps(w, decode_buffers(b), cache, n_seq, past, max_new - 1, b.emb, &g, step_logits ? lg : nullptr,
-                          static_cast<long long>(n_seq) * w->vocab_pad, s);
-    }
-    if ((e = gpt_forward_impl(w, b.emb, n_seq, L, past, cache, b, lg, s))) return e;
     const bool last = step == max_new - 1;
+    if (use_chain_v2(w, n_seq * L)) {
+      float* lg = step_logits ? step_logits + static_cast<size_t>(step) * n_seq * w->vocab_pad : nullptr;
+      if (!rows_ready && (e = chain_add_pos_stats(w, b.emb, cb, n_seq, L, past, s))) return e;
+      if ((e = chain_layers(w, cb, n_seq, L, past, cache, lg, w->vocab_pad, s))) return e;
+      const bool next_chain = !last && use_chain_v2(w, n_seq);
+      if ((e = chain_select(w, cb, n_seq, step, max_new, eos, b.finished, ids_out, len_out, forced_ids, L0 + step, next_chain, b.next, s))) return e;
+      rows_ready = next_chain;
+      continue;
+    }
+    float* lg = step_logits ? step_logits + static_cast<size_t>(step) * n_seq * w->vocab_pad : b.logits;
+    if ((e = gpt_forward_impl(w, b.emb, n_seq, L, past, cache, b, lg, s))) return e;
     if ((e = greedy_select(lg, w->vocab_pad, w->vocab, n_seq, step, max_new, eos, b.finished, ids_out, len_out, forced_ids, w->wte,
                            w->dim, last ? nullptr : b.emb, b.next, s)))
       return e;
+    rows_ready = false;
   }
   return 0;
 }

@@ -248,13 +248,14 @@ __global__ void __maxnreg__(144) gpt_attention_smem_kernel(const __nv_bfloat16* 
                    : "memory");
     }
   };
-  // Without a slot table the cached rows were written by this layer's attention kernels of EARLIER forward calls, i.e.
-  // at least two kernels back in the stream: they are complete before this kernel can start (a programmatic dependent
-  // launch starts only after its predecessor has passed its own wait), so they are requested before the wait and arrive
-  // while the QKV product is still running.  With a slot table (beam search) the table itself may be one kernel old.
+  // Dependents are released at entry (decode_chain.cu: dc_fullk_kernel), so before the wait only data that is a whole
+  // forward call old may be read.  Without a slot table the cached rows were written by this layer's attention kernels of
+  // EARLIER forward calls (dozens of kernels back, and no two full-K products of the chain can be resident together): they
+  // are requested before the wait and arrive while the QKV product is still running.  With a slot table (beam search) the
+  // table itself may be one kernel old.
+  pdl_launch_dependents();
   if (slot == nullptr) stage_cached();
   pdl_wait();
-  pdl_launch_dependents();
   if (slot != nullptr) stage_cached();
   // the L new rows (appended to the cache) and the L query rows
   for (int i = tid; i < L * 24; i += blockDim.x) {
@@ -331,10 +332,17 @@ int gpt_attention(const void* qkv, const float* P, int ksplit, const float* bias
   const double bytes = static_cast<double>(n_seq) * c->heads * GHD * 2.0 * (2.0 * L + 2.0 * (past_len + L));
   if (past_len + L <= ATT_SMEM_MAX_S) {
     const int smem = 2 * (past_len + L) * ATT_ROW_B + L * GHD * 4;
-    static int attr = 0;
-    if (smem > attr && smem > 32 * 1024) {
-      VC_CUDA_OK(cudaFuncSetAttribute(gpt_attention_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_MAX_S * (2 * ATT_ROW_B + GHD * 4)));
-      attr = ATT_SMEM_MAX_S * (2 * ATT_ROW_B + GHD * 4);
+    {
+      // per device (a second GPU in the same process needs its own opt-in); the largest shared-memory carve-out so that these
+      // CTAs can become resident beside the chain's large-shared-memory kernels without the SM re-splitting L1 / shared
+      static bool attr[64] = {false};
+      int dev = 0;
+      VC_CUDA_OK(cudaGetDevice(&dev));
+      if (dev < 0 || dev >= 64 || !attr[dev]) {
+        VC_CUDA_OK(cudaFuncSetAttribute(gpt_attention_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_MAX_S * (2 * ATT_ROW_B + GHD * 4)));
+        VC_CUDA_OK(cudaFuncSetAttribute(gpt_attention_smem_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        if (dev >= 0 && dev < 64) attr[dev] = true;
+      }
     }
     VC_LAUNCH("gpt_attention", bytes, s,
               // one new position per sequence: only one warp computes, so the CTA is that one warp (32 CTAs per SM instead of

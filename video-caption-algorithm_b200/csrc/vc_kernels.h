@@ -96,27 +96,23 @@ int greedy_select(const float* logits, long long ld, int vocab, int n_seq, int s
 int build_prefill_embeds(const float* prefix, const void* wte_bf16, const int32_t* prompt_ids, int n_seq, int P, int Lp,
                          int dim, float* out, cudaStream_t s);
 
-// decode_step.cu — persistent cooperative decode kernel (n_seq <= 128)
-struct DecodeBuffers {
-  float* h; void* xn; void* att; void* hid; float* part; float* cand_v; int* cand_i; unsigned int* bar;
+// decode_chain.cu — the few-row GPT-2 forward as 5 dependent kernels per layer (LayerNorm folded into the consumer
+// products, cluster split-K for the N = H products, lm_head with per-CTA argmax candidates)
+struct ChainBuffers {
+  float* h; void* hb; void* qkv; void* att; void* hid; float* stat; float* cand_v; int* cand_i;
 };
-struct DecodeGreedy {
-  int step0, max_new, eos;
-  int32_t* finished; int32_t* ids_out; int32_t* len_out; const int32_t* forced; int32_t* next_ids;
-};
-bool decode_supported(const VcGptWeights* w, int n_seq, const VcKvCache* c);
-size_t decode_partial_floats_per_row(const VcGptWeights* w);
-// n_steps decode steps starting with input embeddings `emb` (fp32 [n_seq,H], no position) at position past0.
-// greedy != null: argmax + benchmark bookkeeping + feedback on device, steps step0..step0+n_steps-1;
-// greedy == null: one forward step, logits (fp32 [n_seq, vocab_pad]) required.
-int decode_steps(const VcGptWeights* w, const DecodeBuffers& b, const VcKvCache* cache, int n_seq, int past0, int n_steps, const float* emb,
-                 const DecodeGreedy* greedy, float* logits, long long logits_step_stride, cudaStream_t stream);
-
-// decode_lean.cu — persistent decode kernel with symmetric warps (mma.sync + L2-staged partial sums), n_seq <= 64
-bool decode_lean_supported(const VcGptWeights* w, int n_seq, const VcKvCache* c);
-size_t decode_lean_partial_floats_per_row(const VcGptWeights* w);
-int decode_lean_steps(const VcGptWeights* w, const DecodeBuffers& b, float* logits_ws, const VcKvCache* cache, int n_seq, int past0, int n_steps,
-                      const float* emb, const DecodeGreedy* greedy, float* logits, long long logits_step_stride, cudaStream_t stream);
+bool chain_supported(const VcGptWeights* w, int rows);
+int chain_lmhead_ctas();
+// h = embeds + wpe[pos]; hb = bf16(h); stat[0] = row statistics
+int chain_add_pos_stats(const VcGptWeights* w, const float* embeds, const ChainBuffers& b, int n_seq, int L, int past_len, cudaStream_t s);
+// all layers + lm_head (candidates always; logits fp32 [n_seq, ld] when non-null) on rows prepared in h / hb / stat[0]
+int chain_layers(const VcGptWeights* w, const ChainBuffers& b, int n_seq, int L, int past_len, VcKvCache* cache, float* logits, long long ld,
+                 cudaStream_t s);
+// argmax over candidates + greedy bookkeeping (benchmark_baseline.py:210-227) + next step's h / hb / stat[0] rows at next_pos
+int chain_select(const VcGptWeights* w, const ChainBuffers& b, int n_seq, int step, int max_new, int eos, int32_t* finished, int32_t* ids_out,
+                 int32_t* len_out, const int32_t* forced, int next_pos, bool feed_next, int32_t* next_ids, cudaStream_t s);
+int chain_argmax(const ChainBuffers& b, int n_seq, int32_t* out, cudaStream_t s);
+int chain_set_trace(void* buf, int max_records);
 
 // beam_kernels.cu
 int beam_step(const float* logits, long long ld, int vocab, int n_rows, int rows_per_item, const int32_t* seqs, int max_len, int cur_len,

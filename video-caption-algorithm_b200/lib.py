@@ -16,10 +16,12 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 SO_PATH = CSRC / "libvcb200.so"
-SOURCES = ["gemm_tcgen05.cu", "vit_kernels.cu", "resize_kernels.cu", "vit_attention_tc.cu", "gpt2_kernels.cu", "skinny_gemm.cu", "decode_step.cu", "decode_lean.cu", "beam_kernels.cu", "c_abi.cu"]
+SOURCES = ["gemm_tcgen05.cu", "vit_kernels.cu", "resize_kernels.cu", "vit_attention_tc.cu", "gpt2_kernels.cu", "skinny_gemm.cu", "decode_chain.cu", "beam_kernels.cu", "c_abi.cu"]
 HEADERS = ["vc_common.cuh", "vc_kernels.h", "../../include/vcb200.h"]
+# -cudart shared: the runtime is the process's libcudart.so (torch ships one), not a private static copy inside the library
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
+ABI_VERSION = 2          # == vc_abi_version(); bumped with every struct / signature change (include/vcb200.h)
 
 
 class VcError(RuntimeError):
@@ -41,18 +43,43 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """nvcc -gencode arch=compute_100a,code=sm_100a … -> csrc/libvcb200.so (cross-compiles without a GPU)."""
+    """nvcc -gencode arch=compute_100a,code=sm_100a … -> csrc/libvcb200.so (cross-compiles without a GPU).
+    One object per translation unit (only the stale ones are recompiled, in parallel), then one link."""
     if not force and not needs_build():
         return SO_PATH
-    srcs = [str(CSRC / f) for f in SOURCES if (CSRC / f).exists()]
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(SO_PATH), *srcs]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    from concurrent.futures import ThreadPoolExecutor
+    obj_dir = CSRC / "build"
+    obj_dir.mkdir(exist_ok=True)
+    nvcc = _nvcc()
+    hdr_t = max((CSRC / h).stat().st_mtime for h in HEADERS if (CSRC / h).exists())
+    compile_flags = [f for f in NVCC_FLAGS if f not in ("-shared",)]
+    logs = []
+
+    def one(src: str):
+        obj = obj_dir / (src[:-3] + ".o")
+        sp = CSRC / src
+        if not force and obj.exists() and obj.stat().st_mtime > max(sp.stat().st_mtime, hdr_t):
+            return obj, None
+        cmd = [nvcc, *compile_flags, "-c", "-o", str(obj), str(sp)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            return obj, VcError(f"nvcc failed on {src}:\n" + r.stdout + r.stderr)
+        logs.append(r.stderr)
+        return obj, None
+
+    srcs = [f for f in SOURCES if (CSRC / f).exists()]
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        results = list(ex.map(one, srcs))
+    for _, err in results:
+        if err is not None:
+            raise err
+    r = subprocess.run([nvcc, *NVCC_FLAGS, "-o", str(SO_PATH), *[str(o) for o, _ in results]], capture_output=True, text=True)
     if r.returncode != 0:
-        raise VcError("nvcc failed:\n" + r.stdout + r.stderr)
+        raise VcError("nvcc link failed:\n" + r.stdout + r.stderr)
     if verbose:
-        print(r.stderr)
+        print("".join(logs))
     return SO_PATH
 
 
@@ -73,12 +100,13 @@ class VcVitWeights(C.Structure):
 
 class VcGptLayer(C.Structure):
     _fields_ = [(n, _p) for n in ("ln1_g", "ln1_b", "attn_w", "attn_b", "aproj_w", "aproj_b", "ln2_g", "ln2_b",
-                                  "fc_w", "fc_b", "mproj_w", "mproj_b")]
+                                  "fc_w", "fc_b", "mproj_w", "mproj_b",
+                                  "attn_wf", "attn_cs", "attn_bf", "fc_wf", "fc_cs", "fc_bf")]
 
 
 class VcGptWeights(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("dim", "layers", "heads", "vocab", "n_pos", "vocab_pad")] + \
-               [(n, _p) for n in ("wte", "wpe", "lnf_g", "lnf_b")] + [("layer", C.POINTER(VcGptLayer))]
+               [(n, _p) for n in ("wte", "wpe", "lnf_g", "lnf_b", "lmh_w", "lmh_cs", "lmh_b")] + [("layer", C.POINTER(VcGptLayer))]
 
 
 class VcKvCache(C.Structure):
@@ -91,6 +119,7 @@ _SIGNATURES = {
     "vc_abi_version": (_i, []),
     "vc_num_sms": (_i, []),
     "vc_launch_count": (C.c_longlong, []),
+    "vc_debug_trace": (_i, [_p, _i]),
     "vc_prof_begin": (_i, []),
     "vc_prof_end": (_i, [_i, _p, _p, _p, _p]),
     "vc_resize_bilinear_u8": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _p, _p, _i, _p]),
@@ -127,12 +156,9 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     if _lib is not None:
         return _lib
     if build_if_missing and needs_build():
-        # on the GPU box the prebuilt .so travels with the snapshot; rebuild only when stale and nvcc exists
-        try:
-            build()
-        except VcError:
-            if not SO_PATH.exists():
-                raise
+        # on the GPU box the prebuilt .so travels with the snapshot; rebuild when stale.  A failed rebuild is an error:
+        # binding today's signatures to yesterday's binary would run outdated kernels with mismatched argument lists.
+        build()
     if not SO_PATH.exists():
         raise VcError(f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback)")
     lib = C.CDLL(str(SO_PATH))
@@ -140,6 +166,9 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         fn = getattr(lib, name)      # AttributeError here = header/library drift
         fn.restype = res
         fn.argtypes = args
+    got = lib.vc_abi_version()
+    if got != ABI_VERSION:
+        raise VcError(f"{SO_PATH} has ABI version {got}, the Python binding expects {ABI_VERSION}: rebuild the library")
     _lib = lib
     return lib
 
@@ -155,6 +184,7 @@ def ptr(t) -> int:
     return 0 if t is None else t.data_ptr()
 
 
-def current_stream() -> int:
+def current_stream(device=None) -> int:
+    """torch's current stream ON `device` (not on whatever device happens to be current)."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream

@@ -43,9 +43,23 @@ def unwrap_state(state: dict) -> dict:
     return state
 
 
+def fold_layernorm(w: torch.Tensor, bias: torch.Tensor | None, gamma: torch.Tensor, beta: torch.Tensor):
+    """LayerNorm folded into the product that consumes it:  LN(x) W^T + b = rstd * (x W'^T - mean * cs) + b'
+    with W' = bf16(gamma (.) W) [out, in] (what the kernel multiplies), cs[n] = sum_k W'[n][k] (of the ROUNDED weights, so the
+    mean term cancels exactly what the product accumulated) and b' = b + W beta (fp32, from the unrounded weights)."""
+    w = w.detach().double()
+    wf = (w * gamma.detach().double().view(1, -1)).float().to(torch.bfloat16)
+    cs = wf.double().sum(dim=1).float()
+    b2 = w @ beta.detach().double()
+    if bias is not None:
+        b2 = b2 + bias.detach().double()
+    return wf, cs, b2.float()
+
+
 def pack(state: dict, device: torch.device, *, vit_heads: int, gpt_heads: int, gelu: str | None = None) -> PackedModel:
     sd = unwrap_state(state)
     keep: list = []
+    raw = lambda t: _own(keep, t.to(device=device).contiguous())
     bf = lambda t: _own(keep, t.detach().to(device=device, dtype=torch.float32).to(torch.bfloat16).contiguous())
     f32 = lambda t: _own(keep, t.detach().to(device=device, dtype=torch.float32).contiguous())
 
@@ -120,12 +134,19 @@ def pack(state: dict, device: torch.device, *, vit_heads: int, gpt_heads: int, g
         ly.ln2_g, ly.ln2_b = f32(sd[b + "ln_2.weight"]), f32(sd[b + "ln_2.bias"])
         ly.fc_w, ly.fc_b = bf(sd[b + "mlp.c_fc.weight"].t()), f32(sd[b + "mlp.c_fc.bias"])
         ly.mproj_w, ly.mproj_b = bf(sd[b + "mlp.c_proj.weight"].t()), f32(sd[b + "mlp.c_proj.bias"])
+        # decode chain: ln_1 folded into c_attn, ln_2 into c_fc (csrc/decode_chain.cu)
+        wf, cs, b2 = fold_layernorm(sd[b + "attn.c_attn.weight"].t(), sd[b + "attn.c_attn.bias"], sd[b + "ln_1.weight"], sd[b + "ln_1.bias"])
+        ly.attn_wf, ly.attn_cs, ly.attn_bf = raw(wf), raw(cs), raw(b2)
+        wf, cs, b2 = fold_layernorm(sd[b + "mlp.c_fc.weight"].t(), sd[b + "mlp.c_fc.bias"], sd[b + "ln_2.weight"], sd[b + "ln_2.bias"])
+        ly.fc_wf, ly.fc_cs, ly.fc_bf = raw(wf), raw(cs), raw(b2)
     keep.append(glayers)
     gpt = L.VcGptWeights()
     gpt.dim, gpt.layers, gpt.heads, gpt.vocab, gpt.vocab_pad = H, n_gl, gpt_heads, vocab, vocab_pad
     gpt.n_pos = sd[g + "wpe.weight"].shape[0]
     gpt.wte, gpt.wpe = bf(wte_p), f32(sd[g + "wpe.weight"])
     gpt.lnf_g, gpt.lnf_b = f32(sd[g + "ln_f.weight"]), f32(sd[g + "ln_f.bias"])
+    wf, cs, b2 = fold_layernorm(wte_p, None, sd[g + "ln_f.weight"], sd[g + "ln_f.bias"])      # ln_f folded into the tied lm_head
+    gpt.lmh_w, gpt.lmh_cs, gpt.lmh_b = raw(wf), raw(cs), raw(b2)
     gpt.layer = C.cast(glayers, C.POINTER(L.VcGptLayer))
 
     mapper_w = sd["decoder.mapper.0.weight"].detach().to(device=device, dtype=torch.float32).contiguous()
