@@ -47,6 +47,10 @@ typedef struct {
   const float* ln2_g; const float* ln2_b;
   const void* fc1_w;  const float* fc1_b;   /* bf16 [mlp, D] */
   const void* fc2_w;  const float* fc2_b;   /* bf16 [D, mlp] */
+  /* LayerNorm folded into the consumer product (see VcGptLayer): ln_1 into qkv, ln_2 into fc1.  NULL = not packed
+   * (vc_vit_encode then runs the stand-alone residual-add + LayerNorm passes). */
+  const void* qkv_wf; const float* qkv_cs; const float* qkv_bf;
+  const void* fc1_wf; const float* fc1_cs; const float* fc1_bf;
 } VcVitLayer;
 
 typedef struct {

@@ -58,7 +58,7 @@ static inline cudaStream_t S(vc_stream_t s) { return reinterpret_cast<cudaStream
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct VitBuffers {
-  float* x; void* xn; void* qkv; void* att; void* hid; void* delta; void* delta2; float* x_cls; size_t total;
+  float* x; void* xn; void* qkv; void* att; void* hid; void* delta; void* delta2; float* x_cls; float* stats; float* pstats; size_t total;
 };
 static VitBuffers carve_vit(const VcVitWeights* w, int chunk_frames, void* base) {
   const size_t M = static_cast<size_t>(chunk_frames) * w->tokens;
@@ -73,6 +73,8 @@ static VitBuffers carve_vit(const VcVitWeights* w, int chunk_frames, void* base)
   b.delta = p + off;                        off += align_up(M * w->dim * 2, 1024);
   b.delta2 = p + off;                       off += align_up(M * w->dim * 2, 1024);
   b.x_cls = reinterpret_cast<float*>(p + off); off += align_up(static_cast<size_t>(chunk_frames) * w->dim * 4, 1024);
+  b.stats = reinterpret_cast<float*>(p + off); off += align_up(M * 8, 1024);                                     // (mean, rstd) per row
+  b.pstats = reinterpret_cast<float*>(p + off); off += align_up(M * 8 * 3 * ((w->dim + 255) / 256), 1024);      // partial (sum, sum sq)
   b.total = off;
   return b;
 }
@@ -129,7 +131,7 @@ using namespace vc;
 extern "C" {
 
 const char* vc_last_error(void) { return g_err; }
-int vc_abi_version(void) { return 2; }
+int vc_abi_version(void) { return 3; }
 int vc_num_sms(void) {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
@@ -226,6 +228,31 @@ int vc_vit_encode(const VcVitWeights* w, const void* patches_bf16, int n_frames,
     // tokens: [cls + pos0 | conv_proj(patches) + bias + pos]   (video_encoder.py:90-95, Encoder.forward)
     if ((e = cls_rows_init(b.x, w->cls_pos0, nf, N, D, s))) return e;
     if ((e = gemm_bf16(patches, w->patch_w, w->patch_b, nf * P, D, w->patch_k, VC_EPI_PATCH_EMBED, b.x, D, w->pos, P, 0, s))) return e;
+    bool folded = getenv("VC_VIT_UNFOLDED") == nullptr;      // A/B switch: the stand-alone LayerNorm passes of round 1
+    for (int l = 0; l < w->layers; ++l) folded = folded && w->layer[l].qkv_wf != nullptr && w->layer[l].fc1_wf != nullptr;
+    if (folded) {
+      // No LayerNorm pass and no separate residual add.  The residual stream x (fp32) is read-modify-written by the proj and
+      // fc2 epilogues (x += bf16(acc + bias)); both emit bf16(x_new) — the A operand of the next product, whose weights
+      // carry the LayerNorm affine (packing.fold_layernorm) — and partial row statistics; (mean, rstd) are applied in the
+      // consumer's epilogue.  Only the first block's input needs a pass of its own (rows come from two producers).
+      const int parts = 3 * ((D + 255) / 256);
+      const int gelu_f = w->gelu_tanh ? VC_EPI_LNF_GELU_TANH : VC_EPI_LNF_GELU_ERF;
+      if ((e = rowstats_cast(b.x, b.xn, b.stats, M, D, 1e-6f, s))) return e;
+      for (int l = 0; l < w->layers; ++l) {
+        const VcVitLayer& L = w->layer[l];
+        GemmExtra ex{L.qkv_cs, b.stats, nullptr, nullptr, nullptr};
+        if ((e = gemm_bf16_ex(b.xn, L.qkv_wf, L.qkv_bf, M, 3 * D, D, VC_EPI_LNF_BIAS, b.qkv, 3 * D, nullptr, 0, 0, &ex, s))) return e;
+        if (l + 1 == w->layers) break;
+        if ((e = vit_attention(b.qkv, b.att, nf, N, w->heads, 64, s))) return e;
+        GemmExtra ep{nullptr, nullptr, b.x, b.xn, b.pstats};
+        if ((e = gemm_bf16_ex(b.att, L.proj_w, L.proj_b, M, D, D, VC_EPI_RESID_STATS, nullptr, D, nullptr, 0, 0, &ep, s))) return e;
+        if ((e = ln_stats_finalize(b.pstats, parts, M, D, 1e-6f, b.stats, s))) return e;
+        GemmExtra e1{L.fc1_cs, b.stats, nullptr, nullptr, nullptr};
+        if ((e = gemm_bf16_ex(b.xn, L.fc1_wf, L.fc1_bf, M, w->mlp, D, gelu_f, b.hid, w->mlp, nullptr, 0, 0, &e1, s))) return e;
+        if ((e = gemm_bf16_ex(b.hid, L.fc2_w, L.fc2_b, M, D, w->mlp, VC_EPI_RESID_STATS, nullptr, D, nullptr, 0, 0, &ep, s))) return e;
+        if ((e = ln_stats_finalize(b.pstats, parts, M, D, 1e-6f, b.stats, s))) return e;
+      }
+    } else {
     // The bias-added outputs of proj / fc2 go to `delta` / `delta2` in bf16 (write-only epilogues); the LayerNorm kernels
     // fold them into the fp32 residual stream, which is stored once per block (by the next block's LN1).
     bool pending = false;
@@ -243,6 +270,7 @@ int vc_vit_encode(const VcVitWeights* w, const void* patches_bf16, int n_frames,
       if ((e = gemm_bf16(b.xn, L.fc1_w, L.fc1_b, M, w->mlp, D, gelu, b.hid, w->mlp, nullptr, 0, 0, s))) return e;
       if ((e = gemm_bf16(b.hid, L.fc2_w, L.fc2_b, M, D, w->mlp, VC_EPI_BIAS, b.delta2, D, nullptr, 0, 0, s))) return e;
       pending = true;
+    }
     }
     // LAST block: only the class token of each frame is consumed downstream (video_encoder.py:256-258), and every op after
     // the attention is row-wise, so attention runs for the class-token query alone and proj / LN2 / MLP / final LN run on

@@ -43,10 +43,15 @@ constexpr int A_BYTES = BM * BK * 2;          // 16 KB
 constexpr int B_BYTES = (BN / 2) * BK * 2;    // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int TMEM_COLS = 512;         // 2 accumulators x 256 fp32 columns
-constexpr int EPI_WARPS = 12;            // 3 per TMEM lane quarter: column chunks (of 32) 0-2, 3-5, 6-7 of the 256-wide tile
+// Epilogue warps per CTA: a multiple of 4 (a warp reads the TMEM lane quarter warp % 4).  The bf16-output epilogues are
+// instruction-bound (ncu: the GELU epilogue executes 3x the instructions of the bias one and holds the tensor pipe at 68 %
+// active), so they get 16 warps = two 32-column chunks each; the residual + statistics epilogue waits on HBM, keeps a block
+// of residual values in flight per warp (128 registers), and stays at 12 warps (chunks 0-2, 3-5, 6-7).
+__host__ __device__ constexpr int epi_warps(int mode) { return mode == VC_EPI_RESID_STATS ? 12 : 16; }
+constexpr int EPI_WARPS_MAX = 16;
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // one 32x32 fp32 block per warp
-constexpr int THREADS = (2 + EPI_WARPS) * 32;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+__host__ __device__ constexpr int gemm_threads(int mode) { return (2 + epi_warps(mode)) * 32; }
+__host__ __device__ constexpr int gemm_smem(int mode) { return STAGES * STAGE_BYTES + epi_warps(mode) * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/; }
 
 struct GemmParams {
   int M, N, K;
@@ -56,6 +61,12 @@ struct GemmParams {
   int ldo;                // leading dimension of out (elements)
   const float* aux;       // patch-embed: pos embedding [tokens, N]
   int rows_per_group;     // patch-embed: patches per frame (196); out row = g*(rpg+1)+1+r
+  // LayerNorm-folded and residual/statistics epilogues (GemmExtra, vc_kernels.h)
+  const float* cs;        // [N] column sums of the folded weights
+  const float2* stats;    // [M] (mean, rstd) of the rows of A's source
+  float* xres;            // fp32 residual stream [M, N], read-modify-written (RESID_STATS)
+  __nv_bfloat16* xb_out;  // bf16 [M, N]: bf16 copy of the new residual = A operand of the next folded product
+  float2* pstats;         // [parts][M] partial (sum, sum of squares) of the new residual rows, parts = 3 * ceil(N/256)
 };
 
 // Predicated global accesses as single instructions: a C++ `if` around the store lets the compiler sink the whole
@@ -68,6 +79,14 @@ __device__ __forceinline__ void st_pred_v4(void* ptr, float4 v, bool ok) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %0, 0;\n\t@p st.global.v4.f32 [%1], {%2, %3, %4, %5};\n\t}" ::"r"(static_cast<uint32_t>(ok)), "l"(ptr),
                "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
+}
+__device__ __forceinline__ uint2 ld_pred_v2(const void* ptr, bool ok) {
+  uint2 v = make_uint2(0u, 0u);
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p ld.global.v2.b32 {%0, %1}, [%3];\n\t}"
+               : "+r"(v.x), "+r"(v.y)
+               : "r"(static_cast<uint32_t>(ok)), "l"(ptr)
+               : "memory");
+  return v;
 }
 __device__ __forceinline__ float4 ld_pred_v4(const void* ptr, bool ok) {
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -128,14 +147,112 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, uint8_t* stg
   __syncwarp();   // the next block reuses the staging buffer
 }
 
+// ---- LayerNorm folded into this product (A = bf16 of the un-normalised residual, W' = gamma (.) W):
+//      out = act( rstd_row * (acc - mean_row * cs[col]) + bias'[col] )                       (VC_EPI_LNF_*)
+// st[i] = (mean, rstd) of row row_base + 4 i + (lane >> 3): loaded once per tile by the caller (the rows of a warp do not
+// change from one column chunk to the next).
+template <int MODE>
+__device__ __forceinline__ void epilogue_block_lnf(const GemmParams& p, uint8_t* stg, int lane, int row_base, int col0, const uint32_t (&acc)[32],
+                                                   const float2 (&st)[8]) {
+  const uint32_t sbase = smem_u32(stg);
+  const int cc = lane & 7, rsub = lane >> 3;
+  const int col = col0 + cc * 4;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t a = sbase + lane * 128 + ((j ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(acc[4 * j]), "r"(acc[4 * j + 1]), "r"(acc[4 * j + 2]), "r"(acc[4 * j + 3])
+                 : "memory");
+  }
+  __syncwarp();
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+  const float4 c = __ldg(reinterpret_cast<const float4*>(p.cs + col));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + rsub;
+    float4 v;
+    const uint32_t a = sbase + rr * 128 + ((cc ^ (rr & 7)) << 4);
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    const float mean = st[i].x, rstd = st[i].y;
+    v.x = fmaf(rstd, v.x - mean * c.x, b.x); v.y = fmaf(rstd, v.y - mean * c.y, b.y);
+    v.z = fmaf(rstd, v.z - mean * c.z, b.z); v.w = fmaf(rstd, v.w - mean * c.w, b.w);
+    if (MODE == VC_EPI_LNF_GELU_ERF) {
+      v.x = gelu_erf_fast(v.x); v.y = gelu_erf_fast(v.y); v.z = gelu_erf_fast(v.z); v.w = gelu_erf_fast(v.w);
+    } else if (MODE == VC_EPI_LNF_GELU_TANH) {
+      v.x = gelu_tanh_fast(v.x); v.y = gelu_tanh_fast(v.y); v.z = gelu_tanh_fast(v.z); v.w = gelu_tanh_fast(v.w);
+    }
+    const int row = row_base + rr;
+    const bool ok = row < p.M;
+    st_pred_v2(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(ok ? row : 0) * p.ldo + col, pack_bf16(v.x, v.y), pack_bf16(v.z, v.w), ok);
+  }
+  __syncwarp();   // the next block reuses the staging buffer
+}
+
+// ---- VC_EPI_RESID_STATS: the fp32 residual stream is updated HERE,  t = x + bf16(acc + bias);  x = t;  xb_out = bf16(t),
+//      and the rows' (sum, sum of squares) leave as partials, so no stand-alone residual-add / LayerNorm pass over the stream
+//      exists any more.  The Linear output is rounded to bf16 before the fp32 add — what autocast does.
+// The residual values of a block (xv, 8 x 16 bytes per lane) are requested ONE BLOCK AHEAD by the caller — the first block of a
+// tile while its MMAs are still running — so the epilogue does not pay a memory round trip per block (a read-modify-write
+// issued inside the row loop made this product latency-bound in round 1: 250-420 TFLOP/s).
+__device__ __forceinline__ void resid_prefetch(const GemmParams& p, int lane, int row_base, int col0, float4 (&xv)[8]) {
+  const int col = col0 + (lane & 7) * 4, rsub = lane >> 3;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = row_base + i * 4 + rsub;
+    const bool ok = row < p.M && col0 < p.N;
+    xv[i] = ld_pred_v4(p.xres + static_cast<size_t>(ok ? row : 0) * p.N + (ok ? col : 0), ok);
+  }
+}
+__device__ __forceinline__ void epilogue_park(uint8_t* stg, int lane, const uint32_t (&acc)[32]) {
+  const uint32_t sbase = smem_u32(stg);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t a = sbase + lane * 128 + ((j ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(acc[4 * j]), "r"(acc[4 * j + 1]), "r"(acc[4 * j + 2]), "r"(acc[4 * j + 3])
+                 : "memory");
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void epilogue_block_resid(const GemmParams& p, uint8_t* stg, int lane, int row_base, int col0, const float4 (&xv)[8],
+                                                     float (&ssum)[8], float (&ssq)[8]) {
+  const uint32_t sbase = smem_u32(stg);
+  const int cc = lane & 7, rsub = lane >> 3;
+  const int col = col0 + cc * 4;
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + rsub;
+    float4 v;
+    const uint32_t a = sbase + rr * 128 + ((cc ^ (rr & 7)) << 4);
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    const float2 e01 = unpack_bf16(pack_bf16(v.x + b.x, v.y + b.y)), e23 = unpack_bf16(pack_bf16(v.z + b.z, v.w + b.w));
+    const float4 t = make_float4(xv[i].x + e01.x, xv[i].y + e01.y, xv[i].z + e23.x, xv[i].w + e23.y);
+    const int row = row_base + rr;
+    const bool ok = row < p.M;
+    const size_t o = static_cast<size_t>(ok ? row : 0) * p.N + col;
+    st_pred_v4(p.xres + o, t, ok);
+    st_pred_v2(p.xb_out + o, pack_bf16(t.x, t.y), pack_bf16(t.z, t.w), ok);
+    // this row's 32 columns: the 8 lanes that share the row are adjacent
+    float s1 = (t.x + t.y) + (t.z + t.w), s2 = (t.x * t.x + t.y * t.y) + (t.z * t.z + t.w * t.w);
+#pragma unroll
+    for (int o2 = 1; o2 < 8; o2 <<= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o2);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o2);
+    }
+    ssum[i] += s1;
+    ssq[i] += s2;
+  }
+  __syncwarp();   // the next block reuses the staging buffer
+}
+
 template <int MODE>
 // 104 registers x 448 threads leave ~19K registers per SM: one CTA of the decode chain (skinny GEMM: 18.4K) fits beside this kernel
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(80)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(MODE == VC_EPI_RESID_STATS ? 128 : (MODE >= VC_EPI_LNF_BIAS ? 96 : 80))   // x 448 / 576 threads <= 64K registers
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles must sit on 1024-byte boundaries (same offsets in both CTAs of the pair)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;
+  constexpr int EPI_WARPS = epi_warps(MODE);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EPI_WARPS * EPI_STAGE_BYTES);   // used in the leader only
   uint64_t* empty_bar = full_bar + STAGES;    // per CTA: its smem slot is free (multicast commit)
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2] per CTA: accumulator ready (multicast commit)
@@ -222,29 +339,81 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const int ew = warp - 2;            // 0..7
     const int quarter = warp & 3;       // TMEM lane quarter this warp may read
     const int part = ew >> 2;           // which column chunks of the 256-wide tile: 0 -> 0..2, 1 -> 3..5, 2 -> 6..7
-    const int c_begin = part * 3, c_end = part == 2 ? 8 : part * 3 + 3;
+    const int c_begin = EPI_WARPS == 16 ? part * 2 : part * 3, c_end = EPI_WARPS == 16 ? part * 2 + 2 : (part == 2 ? 8 : part * 3 + 3);
     uint8_t* stg = epi_stage + ew * EPI_STAGE_BYTES;
     const uint32_t tempty_leader0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     const uint32_t tempty_leader1 = mapa_shared(smem_u32(&tempty_bar[1]), 0);
     int acc = 0; uint32_t acc_phase = 0;
+    float4 xnext[8];
+    if (MODE == VC_EPI_RESID_STATS && pair < total)
+      resid_prefetch(p, lane, (pair / n_tiles) * (2 * BM) + static_cast<int>(rank) * BM + quarter * 32, (pair % n_tiles) * BN + c_begin * 32, xnext);
     for (int t = pair; t < total; t += n_pairs) {
       const int m0 = (t / n_tiles) * (2 * BM) + static_cast<int>(rank) * BM;
       const int n0 = (t % n_tiles) * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int row_base = m0 + quarter * 32;
+      if (MODE == VC_EPI_RESID_STATS) {
+        float ssum[8], ssq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ssum[i] = ssq[i] = 0.f;
 #pragma unroll 1
-      for (int c = c_begin; c < c_end; ++c) {
-        const int col_in_tile = c * 32;
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_in_tile, r);
-        tmem_ld_wait();
-        const int col0 = n0 + col_in_tile;
-        if (col0 < p.N && row_base < p.M) epilogue_block<MODE>(p, stg, lane, row_base, col0, r);
+        for (int c = c_begin; c < c_end; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, r);
+          tmem_ld_wait();
+          const int col0 = n0 + c * 32;
+          const bool live = col0 < p.N && row_base < p.M;
+          if (live) epilogue_park(stg, lane, r);
+          float4 xcur[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xcur[i] = xnext[i];
+          // the block after this one: next chunk of this tile, or the first chunk of this pair's next tile
+          if (c + 1 < c_end) {
+            resid_prefetch(p, lane, row_base, n0 + (c + 1) * 32, xnext);
+          } else if (t + n_pairs < total) {
+            const int t2 = t + n_pairs;
+            resid_prefetch(p, lane, (t2 / n_tiles) * (2 * BM) + static_cast<int>(rank) * BM + quarter * 32, (t2 % n_tiles) * BN + c_begin * 32, xnext);
+          }
+          if (live) epilogue_block_resid(p, stg, lane, row_base, col0, xcur, ssum, ssq);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+        // partial statistics of this warp's column chunks of this tile: slot (n tile, part) of the row
+        if ((lane & 7) == 0 && n0 + c_begin * 32 < p.N) {
+          float2* ps = p.pstats + static_cast<size_t>((t % n_tiles) * 3 + part) * p.M;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = row_base + i * 4 + (lane >> 3);
+            if (row < p.M) ps[row] = make_float2(ssum[i], ssq[i]);
+          }
+        }
+      } else {
+        float2 st[8];
+        if (MODE >= VC_EPI_LNF_BIAS) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = row_base + i * 4 + (lane >> 3);
+            st[i] = __ldg(p.stats + (row < p.M ? row : 0));
+          }
+        }
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; ++c) {
+          const int col_in_tile = c * 32;
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_in_tile, r);
+          tmem_ld_wait();
+          const int col0 = n0 + col_in_tile;
+          if (col0 < p.N && row_base < p.M) {
+            if (MODE >= VC_EPI_LNF_BIAS) epilogue_block_lnf<MODE>(p, stg, lane, row_base, col0, r, st);
+            else epilogue_block<MODE>(p, stg, lane, row_base, col0, r);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -276,24 +445,25 @@ int make_map(CUtensorMap* tm, const void* ptr, int rows, int K, int box_rows) { 
 
 int g_num_sms = 0;
 std::mutex g_cfg_mu;
-bool g_attr_set[8] = {false};
+bool g_attr_set[16] = {false};
 
 template <int MODE>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t stream) {
   {
     std::lock_guard<std::mutex> lk(g_cfg_mu);
     if (!g_attr_set[MODE]) {
-      VC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      VC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(MODE)));
       // ask for the largest shared-memory carve-out, not the smallest that holds SMEM_BYTES: what is left over (~45 KB)
       // is where the decode chain's CTAs of the previous batch run beside this kernel's resident CTAs (CaptionPipeline)
       VC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       g_attr_set[MODE] = true;
     }
   }
-  static const char* const kNames[] = {"gemm_bias", "gemm_gelu_erf", "gemm_gelu_tanh", "gemm_resid", "gemm_f32", "gemm_patch"};
+  static const char* const kNames[] = {"gemm_bias", "gemm_gelu_erf", "gemm_gelu_tanh", "gemm_resid", "gemm_f32", "gemm_patch",
+                                       "gemm_lnf_bias", "gemm_lnf_gelu_erf", "gemm_lnf_gelu_tanh", "gemm_resid_stats"};
   {
     KernelScope ks(kNames[MODE], 2.0 * p.M * static_cast<double>(p.N) * p.K, stream);
-    gemm_tcgen05_kernel<MODE><<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+    gemm_tcgen05_kernel<MODE><<<grid, gemm_threads(MODE), gemm_smem(MODE), stream>>>(ta, tb, p);
   }
   VC_CUDA_OK(cudaGetLastError());
   return 0;
@@ -320,7 +490,13 @@ int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* ptr, int rows, int K, int
 
 int gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int K, int mode, void* out, int ldo,
               const float* aux, int rows_per_group, int max_ctas, cudaStream_t stream) {
+  return gemm_bf16_ex(A, W, bias, M, N, K, mode, out, ldo, aux, rows_per_group, max_ctas, nullptr, stream);
+}
+
+int gemm_bf16_ex(const void* A, const void* W, const float* bias, int M, int N, int K, int mode, void* out, int ldo,
+                 const float* aux, int rows_per_group, int max_ctas, const GemmExtra* ex, cudaStream_t stream) {
   VC_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  VC_REQUIRE(mode < VC_EPI_LNF_BIAS || (ex != nullptr && bias != nullptr), "gemm: epilogue %d needs the extra operands", mode);
   VC_REQUIRE(K % BK == 0, "gemm: K=%d must be a multiple of %d (pad the operand)", K, BK);
   VC_REQUIRE(N % 32 == 0, "gemm: N=%d must be a multiple of 32", N);
   VC_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
@@ -335,7 +511,12 @@ int gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int
   CUtensorMap ta, tb;
   if (int e = make_map(&ta, A, M, K, BM)) return e;
   if (int e = make_map(&tb, W, N, K, BN / 2)) return e;
-  GemmParams p{M, N, K, mode, bias, out, ldo, aux, rows_per_group};
+  GemmParams p{M, N, K, mode, bias, out, ldo, aux, rows_per_group, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (ex != nullptr) {
+    p.cs = ex->cs; p.stats = reinterpret_cast<const float2*>(ex->stats); p.xres = ex->xres;
+    p.xb_out = static_cast<__nv_bfloat16*>(ex->xb_out);
+    p.pstats = reinterpret_cast<float2*>(ex->pstats);
+  }
   const int total = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);   // pair tiles
   // VC_ENCODER_SMS=n leaves SMs free for kernels of another stream (the decode chain of the previous batch)
   static const int sm_cap = getenv("VC_ENCODER_SMS") ? atoi(getenv("VC_ENCODER_SMS")) : 0;
@@ -352,6 +533,10 @@ int gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int
     case VC_EPI_PATCH_EMBED:
       VC_REQUIRE(aux != nullptr && rows_per_group > 0, "gemm: patch-embed epilogue needs pos embedding and patches/frame");
       return launch<VC_EPI_PATCH_EMBED>(ta, tb, p, grid, stream);
+    case VC_EPI_LNF_BIAS: return launch<VC_EPI_LNF_BIAS>(ta, tb, p, grid, stream);
+    case VC_EPI_LNF_GELU_ERF: return launch<VC_EPI_LNF_GELU_ERF>(ta, tb, p, grid, stream);
+    case VC_EPI_LNF_GELU_TANH: return launch<VC_EPI_LNF_GELU_TANH>(ta, tb, p, grid, stream);
+    case VC_EPI_RESID_STATS: return launch<VC_EPI_RESID_STATS>(ta, tb, p, grid, stream);
     default: set_error("gemm: unknown epilogue mode %d", mode); return -1;
   }
 }

@@ -36,6 +36,21 @@ int resize_bilinear_u8(const uint8_t* src, int n, int H, int W, uint8_t* tmp, ui
                        int ksize_x, const int32_t* ky, const int32_t* by, int ksize_y, cudaStream_t s);
 
 // gemm_tcgen05.cu
+// internal epilogues (continue the public VC_EPI_* numbering): LayerNorm folded into the product, residual update + row statistics
+enum { VC_EPI_LNF_BIAS = 6, VC_EPI_LNF_GELU_ERF = 7, VC_EPI_LNF_GELU_TANH = 8, VC_EPI_RESID_STATS = 9 };
+struct GemmExtra {
+  const float* cs;       // LNF: column sums of the folded weights [N]
+  const float* stats;    // LNF: float2 (mean, rstd) per row of A [M]
+  float* xres;           // RESID_STATS: fp32 residual stream [M, N], x += bf16(acc + bias)
+  void* xb_out;          // RESID_STATS: bf16 copy of the new residual [M, N]
+  float* pstats;         // RESID_STATS: float2 partial (sum, sum of squares) [3 * ceil(N/256)][M]
+};
+int gemm_bf16_ex(const void* A, const void* W, const float* bias, int M, int N, int K, int mode, void* out, int ldo,
+                 const float* aux, int rows_per_group, int max_ctas, const GemmExtra* ex, cudaStream_t stream);
+// float2 (mean, rstd) per row from `parts` partial (sum, sum of squares) pairs over N columns in total
+int ln_stats_finalize(const float* pstats, int parts, int M, int N, float eps, float* stats, cudaStream_t s);
+// xb = bf16(x), stats = (mean, rstd) per row of the fp32 rows x [M, dim]
+int rowstats_cast(const float* x, void* xb_bf16, float* stats, int M, int dim, float eps, cudaStream_t s);
 int gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int K, int mode, void* out, int ldo,
               const float* aux, int rows_per_group, int max_ctas, cudaStream_t stream);
 

@@ -223,10 +223,13 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         }
         mbar_wait(&s_full[t], par);
         tc_fence_after();
+        // A warp whose 32 query rows all lie beyond the frame's tokens (rows 224-255 at 197 tokens) skips both softmax passes:
+        // its TMEM lanes keep the raw scores as "P", the PV MMA turns them into output rows nobody stores.
+        const bool dead = t * 128 + quarter * 32 >= p.tokens;
         // pass 1: row max over the valid keys (64 columns per TMEM load: the loop is latency-, not bandwidth-bound)
         float mx = -INFINITY;
         for (int e = 0; e < p.extra; ++e) mx = fmaxf(mx, sx[e]);
-        int c = 0;
+        int c = dead ? NK : 0;
         for (; c + 64 <= NK; c += 64) {
           uint32_t r[64];
           tmem_ld_32x64(trow + c, r);
@@ -252,7 +255,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         // pass 2: p = 2^(s*scale - m2); row sum in fp32; P as bf16 pairs over S columns this thread has already consumed
         // (keys [c, c+64) -> packed columns [c/2, c/2+32), always at or below the columns being read)
         float sum = 0.f;
-        c = 0;
+        c = dead ? NK : 0;
         for (; c + 64 <= NK; c += 64) {
           uint32_t r[64], pk[32];
           tmem_ld_32x64(trow + c, r);

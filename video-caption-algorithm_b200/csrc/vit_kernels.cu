@@ -249,6 +249,77 @@ int layernorm_f32_bf16(const float* x, const float* g, const float* b, void* out
   return layernorm_rows(x, 1, 0, g, b, nullptr, out, rows, dim, eps, s);
 }
 
+// =========================================================================== row statistics for the LayerNorm-folded GEMMs
+// (mean, rstd) per row from the partial (sum, sum of squares) pairs the residual-updating GEMM epilogues leave behind
+// (gemm_tcgen05.cu: VC_EPI_PROJ_STATS / VC_EPI_FC2_STATS).  Combined in double: the variance is a difference of two sums.
+__global__ void __launch_bounds__(256) ln_stats_finalize_kernel(const float2* __restrict__ ps, int parts, int M, int N, float eps,
+                                                                float2* __restrict__ stats) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  double s = 0.0, q = 0.0;
+  for (int p0 = 0; p0 < parts; p0 += 4) {
+    float2 v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (p0 + i < parts) v[i] = ps[static_cast<size_t>(p0 + i) * M + row];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (p0 + i < parts) { s += v[i].x; q += v[i].y; }
+  }
+  const double mean = s / N;
+  double var = q / N - mean * mean;
+  var = var > 0.0 ? var : 0.0;
+  stats[row] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+}
+int ln_stats_finalize(const float* pstats, int parts, int M, int N, float eps, float* stats, cudaStream_t s) {
+  if (M <= 0) return 0;
+  VC_LAUNCH("ln_stats_finalize", static_cast<double>(M) * (parts + 1) * 8.0, s,
+            (ln_stats_finalize_kernel<<<(M + 255) / 256, 256, 0, s>>>(reinterpret_cast<const float2*>(pstats), parts, M, N, eps,
+                                                                      reinterpret_cast<float2*>(stats))));
+  VC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// xb = bf16(x) and (mean, rstd) of every fp32 row: the entry of the first encoder block (the rows come from the patch-embed
+// GEMM and the class-token init, neither of which sees whole rows).  One warp per row, two-pass statistics in registers.
+__global__ void __launch_bounds__(256) rowstats_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats,
+                                                            int rows, int dim, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float4* src = reinterpret_cast<const float4*>(x + static_cast<long long>(warp) * dim);
+  const int nv = dim >> 7;
+  float4 v[LN_MAX_V4];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i)
+    if (i < nv) {
+      v[i] = src[i * 32 + lane];
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      uint2 w;
+      w.x = pack_bf16(v[i].x, v[i].y);
+      w.y = pack_bf16(v[i].z, v[i].w);
+      reinterpret_cast<uint2*>(xb + static_cast<long long>(warp) * dim)[i * 32 + lane] = w;
+    }
+  const float mean = warp_sum(sum) / static_cast<float>(dim);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i)
+    if (i < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(dim) + eps);
+  if (lane == 0) stats[warp] = make_float2(mean, rstd);
+}
+int rowstats_cast(const float* x, void* xb_bf16, float* stats, int M, int dim, float eps, cudaStream_t s) {
+  VC_REQUIRE(dim % 128 == 0 && dim <= 128 * LN_MAX_V4, "rowstats_cast: dim=%d", dim);
+  if (M <= 0) return 0;
+  VC_LAUNCH("rowstats_cast", static_cast<double>(M) * dim * 6.0, s,
+            (rowstats_cast_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, static_cast<__nv_bfloat16*>(xb_bf16), reinterpret_cast<float2*>(stats), M, dim, eps)));
+  VC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // =========================================================================== class-token rows
 __global__ void cls_rows_kernel(float* __restrict__ x, const float* __restrict__ cls_pos0, int n_frames, int tokens, int dim) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -21,7 +21,7 @@ HEADERS = ["vc_common.cuh", "vc_kernels.h", "../../include/vcb200.h"]
 # -cudart shared: the runtime is the process's libcudart.so (torch ships one), not a private static copy inside the library
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
-ABI_VERSION = 2          # == vc_abi_version(); bumped with every struct / signature change (include/vcb200.h)
+ABI_VERSION = 3          # == vc_abi_version(); bumped with every struct / signature change (include/vcb200.h)
 
 
 class VcError(RuntimeError):
@@ -89,7 +89,8 @@ _p = C.c_void_p
 
 class VcVitLayer(C.Structure):
     _fields_ = [(n, _p) for n in ("ln1_g", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_g", "ln2_b",
-                                  "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+                                  "fc1_w", "fc1_b", "fc2_w", "fc2_b",
+                                  "qkv_wf", "qkv_cs", "qkv_bf", "fc1_wf", "fc1_cs", "fc1_bf")]
 
 
 class VcVitWeights(C.Structure):

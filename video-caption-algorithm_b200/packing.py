@@ -103,6 +103,12 @@ def pack(state: dict, device: torch.device, *, vit_heads: int, gpt_heads: int, g
         ly.ln2_g, ly.ln2_b = f32(sd[b + names["ln2"] + ".weight"]), f32(sd[b + names["ln2"] + ".bias"])
         ly.fc1_w, ly.fc1_b = bf(sd[b + names["fc1"] + ".weight"]), f32(sd[b + names["fc1"] + ".bias"])
         ly.fc2_w, ly.fc2_b = bf(sd[b + names["fc2"] + ".weight"]), f32(sd[b + names["fc2"] + ".bias"])
+        # LayerNorm folded into the consumer GEMM (csrc/gemm_tcgen05.cu VC_EPI_LNF_*): no stand-alone LayerNorm pass in the encoder
+        wf, cs, b2 = fold_layernorm(sd[b + names["qkv_w"]], sd[b + names["qkv_b"]], sd[b + names["ln1"] + ".weight"], sd[b + names["ln1"] + ".bias"])
+        ly.qkv_wf, ly.qkv_cs, ly.qkv_bf = raw(wf), raw(cs), raw(b2)
+        wf, cs, b2 = fold_layernorm(sd[b + names["fc1"] + ".weight"], sd[b + names["fc1"] + ".bias"], sd[b + names["ln2"] + ".weight"],
+                                    sd[b + names["ln2"] + ".bias"])
+        ly.fc1_wf, ly.fc1_cs, ly.fc1_bf = raw(wf), raw(cs), raw(b2)
     keep.append(layers)
     video_dim = sd["encoder.proj.weight"].shape[0]
     vit = L.VcVitWeights()
