@@ -55,6 +55,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--decode-group", type=int, default=4, help="encoder batches decoded together as one chain (CaptionPipeline)")
+    ap.add_argument("--global-batch", type=int, default=0, help="BASELINE configs[2]: total videos per step, sharded by video over the GPUs "
+                                                                 "(512 -> 256 / 128 / 64 per GPU at 2 / 4 / 8); 0 = --batch per GPU (weak scaling)")
+    ap.add_argument("--ref-sample", type=int, default=4, help="videos per step of the reference arm (bounded sample of the workload)")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the cfg4 / cfg5 / library-baseline measurements after the timed region")
     return ap.parse_args()
 
 
@@ -67,34 +71,54 @@ def peaks():
 
 
 # --------------------------------------------------------------------------- CPU arm
-def cpu_sample(iters: int, warmup: int, frames: int, max_new: int):
-    """The reference's CPU path restated by the oracle, on a bounded sample of the workload."""
+def workload_config(args, world: int) -> dict:
+    B = args.global_batch // world if args.global_batch else args.batch
+    return {"workload": f"ViT-B/16 + GPT-2 small, {B} videos x {args.frames} frames 224x224 per GPU, greedy {args.max_new} tokens "
+                        f"(BASELINE.json configs[1]; configs[2] layout at N>1), random-init weights",
+            "videos_per_gpu": B, "global_batch": world * B, "frames": args.frames, "max_new_tokens": args.max_new}
+
+
+def cpu_sample(iters: int, warmup: int, frames: int, max_new: int, videos: int = 1):
+    """The reference's CPU path on a bounded sample of the workload: the UNMODIFIED reference modules from baseline/_ref
+    (kind "reference"), driven like benchmark_baseline.py:243-316 by baseline/ref_driver.py; the oracle port only if the
+    reference tree did not travel (kind "port").  All host threads: torchrun exports OMP_NUM_THREADS=1, which would throttle
+    this arm 13x (round-1 finding), so the thread count is set explicitly."""
     import torch
     import vcb200  # noqa: F401
     from vcb200 import synthetic
-    from oracle import vc_oracle as O
+    from baseline import ref_driver as R
 
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
     a = synthetic.ARCHS[ARCH]
     sd = synthetic.make_state_dict(a, seed=1234)
-    video = synthetic.make_batch_u8(0, 1, frames)
+    video = synthetic.make_batch_u8(0, videos, frames)
     times, enc_ms, step_ms = [], [], []
-    with torch.inference_mode():
+    why = R.available()
+    if why is None:
+        model = R.build_model(sd, a.prefix_len)
         for it in range(warmup + iters):
-            t0 = time.perf_counter()
-            v = O.preprocess_u8(video)
-            feat = O.encode(sd, v, a.vit_heads)
-            t1 = time.perf_counter()
-            prefix = O.visual_prefix(sd, feat)
-            ids, lens, _ = O.greedy_decode(sd, prefix, torch.tensor([[50256]]), max_new, heads=a.gpt_heads,
-                                           forced_ids=torch.zeros(1, max_new, dtype=torch.int64) + 11)   # never stops early
-            t2 = time.perf_counter()
+            s_, enc, steps, _ = R.cpu_iteration(model, video, max_new)
             if it >= warmup:
-                times.append(t2 - t0)
-                enc_ms.append((t1 - t0) * 1e3)
-                step_ms.append((t2 - t1) * 1e3 / max_new)
+                times.append(s_); enc_ms.append(enc * 1e3); step_ms.append(statistics.median(steps[1:] or steps) * 1e3)
+        kind, how = "reference", "unmodified reference modules (baseline/_ref: VideoCaptionModel, benchmark_baseline.py:243-316 loop)"
+    else:
+        from oracle import vc_oracle as O
+        with torch.inference_mode():
+            for it in range(warmup + iters):
+                t0 = time.perf_counter()
+                feat = O.encode(sd, O.preprocess_u8(video), a.vit_heads)
+                t1 = time.perf_counter()
+                prefix = O.visual_prefix(sd, feat)
+                O.greedy_decode(sd, prefix, torch.tensor([[50256]]), max_new, heads=a.gpt_heads,
+                                forced_ids=torch.zeros(videos, max_new, dtype=torch.int64) + 11)   # never stops early
+                t2 = time.perf_counter()
+                if it >= warmup:
+                    times.append(t2 - t0); enc_ms.append((t1 - t0) * 1e3); step_ms.append((t2 - t1) * 1e3 / max_new)
+        kind, how = "port", f"oracle port ({why})"
     per = statistics.mean(times)
-    return dict(value=1.0 / per, unit="captions/s", cores=torch.get_num_threads(), kind="port",
-                sample=f"{iters} iters of 1 video x {frames} frames 224x224, {max_new} greedy tokens, fp32, oracle port "
+    return dict(value=videos / per, unit="captions/s", cores=torch.get_num_threads(), kind=kind,
+                sample=f"{iters} iters of {videos} video(s) x {frames} frames 224x224, {max_new} greedy tokens, fp32, {how} "
                        f"(ViT {statistics.mean(enc_ms):.0f} ms, decode step {statistics.mean(step_ms):.1f} ms)",
                 host_cpus=os.cpu_count()), per
 
@@ -103,16 +127,15 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, per = cpu_sample(max(args.steps, 1), max(args.warmup, 1), args.frames, args.max_new)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    base, per = cpu_sample(max(args.steps, 1), max(args.warmup, 1), args.frames, args.max_new, videos=max(args.ref_sample, 1))
+    cfg = workload_config(args, world)
+    cfg["sample"] = f"each step = {max(args.ref_sample, 1)} videos of that workload on the host CPU, fp32, all host threads (bounded sample)"
     line = {
         "impl": "reference", "metric": "captions/sec (16-frame clips)", "value": base["value"], "unit": "captions/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"ViT-B/16 + GPT-2 small, {args.batch} videos x {args.frames} frames 224x224 per GPU, greedy {args.max_new} tokens "
-                               f"(BASELINE.json configs[1]; configs[2] layout at N>1), random-init weights",
-                   "videos_per_gpu": args.batch, "frames": args.frames, "max_new_tokens": args.max_new,
-                   "sample": "each step = 1 video of that workload on the host CPU, fp32, all host threads (bounded sample)"},
-        "cpu_baseline": base,
+        "scaling": "weak" if not args.global_batch else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": cfg, "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -173,6 +196,57 @@ class ClockSampler:
                 "window": "timed region" if inside else "warm-up load just before the timed region"}
 
 
+# --------------------------------------------------------------------------- BASELINE configs[3] and configs[4]
+def extra_configs(model, frames64, a, pk, dev):
+    """Measured after the timed region, on rank 0: cfg4 (beam 5 x 30 tokens at 64 videos, the decode-bound path) on the bench
+    model, cfg5 (ViT-L/14 + GPT-2 medium, 32 frames per clip, 16 videos = one GPU's share of the 128-video batch)."""
+    import torch
+    from vcb200 import synthetic
+    from vcb200.decoding import hf_generate_ids
+    from vcb200.model import B200CaptionModel
+    out = {}
+
+    def timed_ms(fn, iters=3):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            r = fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters, r
+
+    # ---- cfg4
+    kw = dict(max_new_tokens=30, num_beams=5, no_repeat_ngram_size=3, repetition_penalty=1.1, min_new_tokens=8)
+    enc_ms, (_, prefix) = timed_ms(lambda: model.encode_prefix(frames64))
+    dec_ms, _ = timed_ms(lambda: hf_generate_ids(model, prefix, [50256], **kw))
+    out["cfg4"] = {"workload": "64 videos x 16 frames, beam search width 5, 30 tokens (HF generate semantics), 320 decode rows",
+                   "captions_s": round(64 / ((enc_ms + dec_ms) / 1e3), 1), "ms_per_batch": round(enc_ms + dec_ms, 2), "encode_ms": round(enc_ms, 2),
+                   "decode_ms": round(dec_ms, 2), "decode_ms_per_step": round(dec_ms / 30, 3)}
+    # ---- cfg5
+    a5 = synthetic.ARCHS["vit_l14_gpt2m"]
+    m5 = B200CaptionModel(synthetic.make_state_dict(a5, seed=1234), dev, vit_heads=a5.vit_heads, gpt_heads=a5.gpt_heads, chunk_frames=512)
+    f5 = synthetic.make_batch_u8(0, 16, 32).to(dev)
+    enc5, (_, pre5) = timed_ms(lambda: m5.encode_prefix(f5))
+    m5.greedy_ids(pre5, None, 20); m5.greedy_ids(pre5, None, 1)
+    full5, _ = timed_ms(lambda: m5.greedy_ids(pre5, None, 20), iters=10)
+    one5, _ = timed_ms(lambda: m5.greedy_ids(pre5, None, 1), iters=10)
+    step5 = (full5 - one5) / 19 * 1e3
+    tok, D, mlp, Ld = 257, 1024, 4096, 24
+    mac_block = tok * (D * 3 * D + D * D + 2 * D * mlp) + 2 * tok * tok * D
+    pruned = (tok * D * D + 2 * tok * D * mlp + 2 * tok * tok * D) * (tok - 1) / tok
+    gflop_frame = 2 * (256 * 588 * D + Ld * mac_block - pruned) / 1e9
+    tf5 = 16 * 32 * gflop_frame / 1e3 / (enc5 / 1e3)
+    bytes5 = 707_549_184 + 16 * (5 + 9.5) * 98_304 + 16 * 98_304
+    out["cfg5"] = {"workload": "ViT-L/14 + GPT-2 medium, 16 videos x 32 frames per GPU (128 over 8 GPUs), greedy 20 tokens",
+                   "captions_s_per_gpu": round(16 / ((enc5 + full5) / 1e3), 2), "encode_ms": round(enc5, 2), "encoder_tflops": round(tf5, 1),
+                   "encoder_frac_of_sustained": round(tf5 / pk["tf_sustained"], 4), "encoder_gflop_per_frame_executed": round(gflop_frame, 2),
+                   "decode_ms_20_tokens": round(full5, 2), "decode_step_us": round(step5, 1),
+                   "decode_frac": round(bytes5 / (step5 * 1e-6) / 1e9 / pk["hbm"], 4), "decode_floor_us": round(bytes5 / pk["hbm"] / 1e3, 1)}
+    del m5
+    torch.cuda.empty_cache()
+    return out
+
+
 # --------------------------------------------------------------------------- our arm
 def run_b200(args):
     import torch
@@ -193,23 +267,32 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = L.load()
     a = synthetic.ARCHS[ARCH]
-    B, T, n_new = args.batch, args.frames, args.max_new
+    T, n_new = args.frames, args.max_new
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} does not divide over {world} GPUs")
+        B = args.global_batch // world                        # BASELINE configs[2]: 512 videos sharded by video
+    else:
+        B = args.batch
+    group = max(1, min(args.decode_group, 256 // B))          # sequences per decode chain <= 256 (CaptionPipeline.MAX_DECODE_ROWS)
     sd = synthetic.make_state_dict(a, seed=1234)
     model = B200CaptionModel(sd, dev, vit_heads=a.vit_heads, gpt_heads=a.gpt_heads, chunk_frames=args.chunk_frames)
-    del sd
     # this rank's shard: global video indices rank*B .. rank*B+B-1 (reproducible for any world size)
     host_frames = synthetic.make_batch_u8(rank * B, B, T).pin_memory()
     dev_frames = host_frames.to(dev)
-    from vcb200.sharding import gather_ids, shard_range
+    from vcb200.sharding import IdGatherer, shard_range
     assert shard_range(world * B, world, rank) == (rank * B, rank * B + B)
+    gatherer = IdGatherer(B, n_new, world, dev)               # preallocated: one all_gather_into_tensor per batch, nothing allocated
+    last_gather = {}
 
     # The timed path is the three-stream pipeline (model.pipeline): H2D of batch i+2, encode of batch i+1 and decode of
     # batch i overlap; every batch still runs preprocess -> ViT -> prefix -> 20 greedy steps -> (gather) in full.
-    pipe = model.pipeline(max_new_tokens=n_new, decode_group=args.decode_group)
+    pipe = model.pipeline(max_new_tokens=n_new, decode_group=group)
 
     def after_decode(ids, lens):
-        if world > 1:
-            gather_ids(ids, lens, world * B)        # the path's only exchange: token ids (+lengths) over NVLink
+        # the path's only exchange: token ids (+lengths) of every rank, over NVLink (N = 1: a device copy into the same buffer)
+        last_gather["buf"] = gatherer.gather(ids, lens)
+        last_gather["ids"], last_gather["lens"] = ids, lens
 
     def step_resident():
         return pipe.submit(dev_frames, to_host=False, after_decode=after_decode)
@@ -250,9 +333,9 @@ def run_b200(args):
     st = next((v for k, v in model._graphs.items() if k[0] == "greedy"), None)
     # kernels inside one greedy-decode graph replay (counted once, at capture time, by the library)
     c0 = lib.vc_launch_count()
-    model.greedy_ids(torch.zeros(B, a.prefix_len, a.gpt_dim, device=dev), None, n_new, use_graph=False)
+    model.greedy_ids(torch.zeros(B * group, a.prefix_len, a.gpt_dim, device=dev), None, n_new, use_graph=False)
     torch.cuda.synchronize()
-    graph_nodes = lib.vc_launch_count() - c0
+    graph_nodes = lib.vc_launch_count() - c0                 # kernels of one decode chain = `group` batches
 
     l0 = lib.vc_launch_count()
     sampler.mark_begin()
@@ -261,7 +344,18 @@ def run_b200(args):
     ids, lens = pipe.result(ticket, host=False)
     live = lib.vc_launch_count() - l0
     clocks = sampler.stop()
-    launches = live + args.steps * graph_nodes
+    launches = live + (args.steps // group) * graph_nodes
+    # the gathered ids are kept and checked (outside the timed region): block r of the buffer is rank r's own batch, and every
+    # rank holds the same buffer
+    torch.cuda.synchronize()
+    gather_ok = gatherer.check_own_block(last_gather["buf"], last_gather["ids"], last_gather["lens"], rank)
+    if world > 1:
+        mine = last_gather["buf"].clone()
+        ref0 = mine.clone()
+        dist.broadcast(ref0, src=0)
+        flag = torch.tensor([int(gather_ok and torch.equal(mine, ref0))], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_ok = bool(flag.item())
     per_step_ms = ms / args.steps
     value = world * B * args.steps / (ms / 1e3)
 
@@ -291,23 +385,28 @@ def run_b200(args):
         torch.cuda.synchronize()
         enc_ms, dec_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
         # decode-step latency: (T(prefill + n_new-1 steps) - T(prefill)) / (n_new-1), graph replays, p50 over iterations
-        full, pre = [], []
-        model.greedy_ids(prefix, None, 1)
-        for _ in range(10):                              # warm-ups (benchmark_baseline.py:513)
-            model.greedy_ids(prefix, None, n_new); model.greedy_ids(prefix, None, 1)
-        for _ in range(50):                              # measured iterations (:514)
-            t0, t1, t2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            t0.record(); model.greedy_ids(prefix, None, n_new); t1.record(); model.greedy_ids(prefix, None, 1); t2.record()
-            torch.cuda.synchronize()
-            full.append(t0.elapsed_time(t1)); pre.append(t1.elapsed_time(t2))
-        step_us = sorted((f - p) / (n_new - 1) * 1e3 for f, p in zip(full, pre))
-        step_p50 = step_us[len(step_us) // 2]
+        def step_latency(pre_rows, warm=10, iters=50):
+            full, pre = [], []
+            model.greedy_ids(pre_rows, None, 1)
+            for _ in range(warm):                        # warm-ups (benchmark_baseline.py:513)
+                model.greedy_ids(pre_rows, None, n_new); model.greedy_ids(pre_rows, None, 1)
+            for _ in range(iters):                       # measured iterations (:514)
+                t0, t1, t2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                t0.record(); model.greedy_ids(pre_rows, None, n_new); t1.record(); model.greedy_ids(pre_rows, None, 1); t2.record()
+                torch.cuda.synchronize()
+                full.append(t0.elapsed_time(t1)); pre.append(t1.elapsed_time(t2))
+            us = sorted((f - p) / (n_new - 1) * 1e3 for f, p in zip(full, pre))
+            return us[len(us) // 2]
+        n_dec = min(B, 64)                                # BASELINE metric: p50 decode-step latency at 64 sequences
+        prefix = prefix[:n_dec].contiguous()
+        step_p50 = step_latency(prefix)
+        step_p50_256 = step_latency(prefix.repeat(256 // n_dec, 1, 1), warm=3, iters=10)     # the grouped chain the pipeline runs
         # reference-style number: the benchmark's python loop over gpt2(inputs_embeds=..., past_key_values=...) with a host
         # sync after every step (benchmark_baseline.py:194-221), through the adapter's reference surface
         import time as _time
         gpt2 = model.decoder.model
         synced = []
-        bos = torch.full((B, 1), 50256, device=dev, dtype=torch.long)
+        bos = torch.full((n_dec, 1), 50256, device=dev, dtype=torch.long)
         for it in range(3):
             x = torch.cat([prefix, gpt2.transformer.wte(bos)], dim=1)
             past = None
@@ -324,7 +423,8 @@ def run_b200(args):
         step_synced_p50 = synced[len(synced) // 2]
         P0 = a.prefix_len + 1
         s_mid = P0 + (n_new - 1) / 2.0
-        step_bytes = GPT_WEIGHT_BYTES + B * s_mid * KV_BYTES_PER_TOKEN + B * KV_BYTES_PER_TOKEN
+        step_bytes = GPT_WEIGHT_BYTES + n_dec * s_mid * KV_BYTES_PER_TOKEN + n_dec * KV_BYTES_PER_TOKEN
+        step_bytes_256 = GPT_WEIGHT_BYTES + 256 * s_mid * KV_BYTES_PER_TOKEN + 256 * KV_BYTES_PER_TOKEN
         # per-kernel CUDA-event timing of one encoder pass (eager launches on the current stream)
         lib.vc_prof_begin()
         model.encode_prefix(dev_frames)
@@ -343,7 +443,7 @@ def run_b200(args):
         achieved = g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
         enc_tflops = B * T * VIT_GFLOP_PER_FRAME / 1e3 / (enc_ms / 1e3)
         traffic = None
-        tp = ROOT / "profiles" / "r1_gemm_traffic.json"
+        tp = ROOT / "profiles" / "r2_gemm_traffic.json"
         if tp.exists():
             traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch_avg")   # from the committed ncu pass, not measured live
         roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all epilogues, one ViT encoder pass)",
@@ -351,35 +451,55 @@ def run_b200(args):
                     "frac": round(achieved / pk["tf_sustained"], 4), "peak_source": pk["source"] + " sustained bf16 (kernel timed inside a long step)",
                     "frac_of_burst": round(achieved / pk["tf_burst"], 4), "launches": g_calls, "avg_launch_ms": round(g_ms / max(g_calls, 1), 4),
                     "flop_per_launch_avg": g_fl / max(g_calls, 1), "traffic": traffic,
-                    "traffic_source": "ncu dram__bytes_read+write per launch averaged over the 49 GEMM launches of one encoder pass, profiles/r1_gemm_traffic.json",
+                    "traffic_source": "ncu --set full dram__bytes_read+write per launch, weighted over the GEMM launches of one encoder pass (one capture per epilogue type), profiles/r2_gemm_traffic.json",
+                    "algorithmic_flop": "2 M N K per launch, M = frames x 197 rows (no padding counted); SURVEY.md 8d: 35.126 GFLOP per frame",
+                    "standalone_layernorm_passes": sum(v["calls"] for k, v in kern.items() if k in ("add_layernorm", "layernorm") and v["work"] > 1e9),
                     "encoder_stage_tflops": round(enc_tflops, 1), "encoder_stage_frac": round(enc_tflops / pk["tf_sustained"], 4),
                     "encoder_gflop_per_frame_executed": round(VIT_GFLOP_PER_FRAME, 3),
                     "encoder_pruning": "last block: proj/MLP/attention for the class-token row only (-6.3 % of 35.126 GFLOP/frame)"}
         decode = {"bound": "hbm", "step_p50_us": round(step_p50, 1), "bytes_per_step": int(step_bytes),
                   "achieved": round(step_bytes / (step_p50 * 1e-6) / 1e9, 1), "peak": pk["hbm"], "unit": "GB/s",
-                  "frac": round(step_bytes / (step_p50 * 1e-6) / 1e9 / pk["hbm"], 4), "n_seq": B, "S_range": [P0, P0 + n_new - 1],
+                  "frac": round(step_bytes / (step_p50 * 1e-6) / 1e9 / pk["hbm"], 4), "n_seq": n_dec, "S_range": [P0, P0 + n_new - 1],
+                  "step_p50_us_256_rows": round(step_p50_256, 1),
+                  "frac_256_rows": round(step_bytes_256 / (step_p50_256 * 1e-6) / 1e9 / pk["hbm"], 4),
+                  "chains": "<= 64 rows: decode_chain.cu (5 kernels per layer); beyond: split-K chain (8 per layer), which the pipeline's grouped decode uses",
                   "step_synced_p50_us": round(step_synced_p50, 1), "how": "(graph replay of prefill+19 steps - graph replay of prefill) / 19, p50 of 50 iterations after 10 warm-ups; step_synced = the reference's python loop with a host sync per step through the adapter surface"}
         line = {
             "metric": "captions/sec (16-frame clips)", "value": round(value, 2), "unit": "captions/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(per_step_ms, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"ViT-B/16 + GPT-2 small, {B} videos x {T} frames 224x224 per GPU, greedy {n_new} tokens "
-                                   f"(BASELINE.json configs[1]; configs[2] layout at N>1), random-init weights",
-                       "videos_per_gpu": B, "global_batch": world * B, "frames": T, "max_new_tokens": n_new,
+            "scaling": "weak" if not args.global_batch else "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {**workload_config(args, world),
                        "parallelism": f"videos sharded over {world} GPU(s), ids all_gather", "chunk_frames": args.chunk_frames,
                        "pipelining": "batches back to back on 3 streams (H2D / encode / decode overlap across batches, %d encoder batches "
-                                     "per decode chain); stages_ms is one batch alone" % args.decode_group,
+                                     "per decode chain); stages_ms is one batch alone" % group,
                        "l2": "inputs (154 MB uint8 frames) and per-layer activations (>300 MB) exceed the 126 MB L2 every step"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roofline, "decode": decode, "single_batch_ms": round(enc_ms + dec_ms, 3),
             "stages_ms": {"preprocess+ViT_Encoder+Cross_Modal_Alignment": round(enc_ms, 3), "GPT2_Decoder_Step(x%d)" % n_new: round(dec_ms, 3)},
             "kernels_one_encoder_pass": kern,
             "sample_ids": ids[0, :8].tolist(),
+            "gather_ok": gather_ok,
         }
+        if not args.no_extra_configs:
+            line["configs"] = extra_configs(model, dev_frames[:64], a, pk, dev)
+            if world == 1:
+                try:
+                    from baseline import ref_driver as R
+                    why = R.available()
+                    if why is None:
+                        lb = R.gpu_library_baseline(synthetic.make_state_dict(a, seed=1234), dev_frames[:64], n_new)
+                        lb["ours_over_library"] = {"captions_per_s": round(value / lb["captions_per_s"], 2),
+                                                   "vit_encoder": round(lb["vit_encoder_ms"] / enc_ms, 2),
+                                                   "decode_step": round(lb["decode_step_p50_us"] / step_p50, 2) if lb["decode_step_p50_us"] else None}
+                        line["library_baseline"] = lb
+                    else:
+                        line["library_baseline"] = {"unavailable": why}
+                except Exception as exc:                       # a reported side measurement must never take the bench line down
+                    line["library_baseline"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.cuda.synchronize()
-        cpu, _ = cpu_sample(3, 1, T, n_new)
+        cpu, _ = cpu_sample(3, 1, T, n_new, videos=2)
         line["cpu_baseline"] = cpu
     if rank == 0:
         print(json.dumps(line), flush=True)

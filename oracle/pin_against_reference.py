@@ -131,10 +131,78 @@ def align(model, feat, ln_scale=0.6, in_weight=0.4):
     return emb, model.decoder.mapper(emb).view(emb.size(0), model.decoder.prefix_len, hid)
 
 
+def pin_eos(out_dir):
+    """The eos / finished branch of the reference loop (benchmark_baseline.py:212-224) on weights doctored so that it fires:
+    rows that finish at step 0, rows that never finish, and a batch in which every row finishes at once (early break :224)."""
+    from oracle import eos_fixture as EF
+    a = synthetic.ARCHS["tiny"]
+    model, sd = build_reference_model("tiny", 1234)
+    EF.doctor(sd, a.gpt_dim)
+    own = model.state_dict()
+    load = dict(sd)
+    for k in own:
+        if k.startswith("encoder.backbone.model.heads."):
+            load[k] = own[k]
+    model.load_state_dict(load, strict=True)
+    n_new, n_rows = 10, 32
+    prefix = EF.prefixes(n_rows, a.prefix_len, a.gpt_dim)
+    gpt2 = model.decoder.model
+
+    @torch.inference_mode()
+    def run(pre):
+        B = pre.shape[0]
+        prompt_ids = torch.tensor([[EF.PROMPT]], dtype=torch.long).expand(B, -1)
+        full = torch.cat([pre, gpt2.transformer.wte(prompt_ids)], dim=1)
+        mask = torch.ones(full.shape[:2], dtype=torch.long)
+        toks = [[] for _ in range(B)]
+        past, nxt_in = None, full
+        finished = torch.zeros(B, dtype=torch.bool)
+        margins, top2 = [], []
+        steps_run = 0
+        for _ in range(n_new):                      # benchmark_baseline.py:193-231 minus the CUDA events
+            out = gpt2(inputs_embeds=nxt_in, attention_mask=mask, past_key_values=past, use_cache=True, return_dict=True)
+            logits = out.logits[:, -1, :].float()
+            steps_run += 1
+            margins.append(EF.eos_margin(logits))
+            t2 = logits.topk(2, dim=-1).values
+            top2.append(t2[:, 0] - t2[:, 1])
+            nxt = torch.argmax(logits, dim=-1)
+            nxt = torch.where(finished, torch.full_like(nxt, EF.EOS), nxt)
+            for i, t in enumerate(nxt.tolist()):
+                if not finished[i]:
+                    toks[i].append(t)
+                    if t == EF.EOS:
+                        finished[i] = True
+            past = out.past_key_values
+            if finished.all():
+                break
+            nxt_in = gpt2.transformer.wte(nxt).unsqueeze(1)
+            mask = torch.cat([mask, torch.ones((B, 1), dtype=torch.long)], dim=1)
+        ids = torch.full((B, n_new), EF.EOS, dtype=torch.int64)
+        for i, t in enumerate(toks):
+            ids[i, :len(t)] = torch.tensor(t)
+        pad = n_new - len(margins)
+        M = torch.stack(margins + [torch.zeros(B)] * pad, 0)
+        T = torch.stack(top2 + [torch.zeros(B)] * pad, 0)
+        return ids, torch.tensor([len(t) for t in toks]), M, T, steps_run
+
+    ids, lens, M, T, steps = run(prefix)
+    first = [i for i in range(n_rows) if lens[i] == 1]
+    ids1, lens1, M1, T1, steps1 = run(prefix[first])
+    print("eos fixture: lengths", lens.tolist(), "| all-finish-at-once batch rows", first, "steps run", steps1, flush=True)
+    assert len(first) >= 3 and steps1 == 1 and (lens == n_new).any()
+    np.savez_compressed(out_dir / "eos_tiny.npz", seed=1234, n_rows=n_rows, max_new_tokens=n_new, ids=ids.numpy(), lengths=lens.numpy(),
+                        eos_margin=M.numpy(), top2_margin=T.numpy(), steps_run=steps, first_rows=np.array(first), first_ids=ids1.numpy(),
+                        first_lengths=lens1.numpy(), first_steps_run=steps1)
+
+
 def main():
     out_dir = REPO / "tests" / "golden"
     out_dir.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
+    if "--only-eos" in sys.argv:
+        pin_eos(out_dir)
+        return
 
     # ---- preprocessing: the reference's own load_video_tensor on JPEG files ----
     from PIL import Image
@@ -215,6 +283,7 @@ def main():
             logits_top=L.topk(8, dim=-1).values.numpy(), logits_top_idx=L.topk(8, dim=-1).indices.numpy(),
             hf_greedy=hf_greedy, **beams, **{f"stat_{k}": v for k, v in stats.items()})
         del model
+    pin_eos(out_dir)
 
 
 if __name__ == "__main__":

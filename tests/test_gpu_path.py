@@ -144,24 +144,6 @@ def test_batch_and_chunk_invariance_at_cfg_sizes():
     assert torch.equal(ids_again, ids_all)
 
 
-def test_eos_bookkeeping_forced():
-    """benchmark_baseline.py:212-224: a row stops at its first eos, later slots stay eos, length counts the eos."""
-    a, sd, m = _model("tiny")
-    prefix = torch.randn(3, 4, 768, device=DEV) * 0.1
-    ids, lens, logits = m.greedy_ids(prefix, None, 5, keep_logits=True)
-    torch.cuda.synchronize()
-    lg = logits.clone()
-    # re-run selection on doctored logits through the same kernel path: make row 1 emit eos at step 0 via argmax API
-    from vcb200 import lib as L
-    row = lg[0, 1].clone().contiguous()
-    row[50256] = row.max() + 1
-    out = torch.empty(1, device=DEV, dtype=torch.int32)
-    L.check(L.load().vc_argmax_f32(row.data_ptr(), 1, 50257, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
-    torch.cuda.synchronize()
-    assert out.item() == 50256
-    assert lens.cpu().tolist() == [5, 5, 5] or all(1 <= v <= 5 for v in lens.cpu().tolist())
-
-
 def test_no_cpu_fallback():
     from vcb200 import lib as L
     a = synthetic.ARCHS["tiny"]
@@ -226,8 +208,9 @@ def test_beam_search_against_reference_golden(golden_dir):
         m, torch.from_numpy(g["prefix"]).to(DEV), [50256], max_new_tokens=24, num_beams=3)
     torch.cuda.synchronize()
     got = ids.cpu()[:, : ref.shape[1]]
-    # free-running beams in bf16 vs the fp32 reference can fork at a near-tie; the first tokens must agree
-    assert got[:, :4].tolist() == ref[:, :4].tolist()
+    # free-running beams in bf16 vs the fp32 reference can fork at a near-tie; up to the fork all 24 positions are identical
+    fork = [next((i for i in range(ref.shape[1]) if int(got[b, i]) != int(ref[b, i])), ref.shape[1]) for b in range(ref.shape[0])]
+    assert min(fork) >= 4 and sum(fork) / len(fork) >= 0.5 * ref.shape[1], fork
 
 
 def test_vit_l14_gpt2_medium_shapes_against_oracle():
@@ -275,16 +258,23 @@ def test_engine_three_candidates_encode_once():
     sd = synthetic.make_state_dict(a, seed=1234)
     eng = InferenceEngine(InferenceConfig(device=DEV, num_frames=2), state_dict=sd)
     frames = synthetic.make_batch_u8(0, 2, 2).to(DEV)
-    c0 = L.load().vc_launch_count()
+    import ctypes as C
+    lib = L.load()
+    lib.vc_prof_begin()
     out = eng.infer_frames(frames)
     torch.cuda.synchronize()
+    mx = 64
+    names = C.create_string_buffer(mx * 48); tms = (C.c_float * mx)(); calls = (C.c_int * mx)(); work = (C.c_double * mx)()
+    n = lib.vc_prof_end(mx, names, tms, calls, work)
+    launched = {names.raw[i * 48:(i + 1) * 48].split(b"\0")[0].decode(): calls[i] for i in range(n)}
     assert set(out) == {"S1", "S2", "S3"}
     assert out["S1"]["ids"].shape == (2, preset_to_kwargs("precise")["max_new_tokens"])
     assert all(8 <= int(n) <= 24 for n in out["S1"]["lengths"].tolist())     # min_new_tokens=8 (text_decoder.py:116)
     assert out["S1"]["ids"].tolist() == out["S2"]["ids"].tolist()             # same preset, same (bos) prompt without a tokenizer
-    # the ViT ran once: exactly one preprocess launch
-    m2 = L.load().vc_launch_count() - c0
-    assert m2 > 0
+    # three candidates, ONE encode (the reference re-encodes per candidate, core/engine.py:43): one preprocess launch, one
+    # patch-embed GEMM, one pool/prefix kernel
+    assert sum(v for k, v in launched.items() if k.startswith("preprocess")) == 1, launched
+    assert launched.get("gemm_patch") == 1 and launched.get("pool_prefix") == 1, launched
     with pytest.raises(ValueError):
         InferenceEngine(InferenceConfig(device=DEV, backend="tensorrt"), state_dict=sd)
 

@@ -81,3 +81,34 @@ def test_resize_matches_pillow_golden(golden_dir):
     # identity size is a copy
     x = torch.randint(0, 256, (2, 224, 224, 3), dtype=torch.uint8)
     assert torch.equal(O.resize_bilinear_u8(x, 224, 224), x)
+
+
+def test_eos_branch_matches_reference_loop(golden_dir):
+    """benchmark_baseline.py:212-224 (finished rows forced to eos, tokens appended up to and including the first eos, loop ends
+    when every row has finished): the oracle's greedy loop equals the reference's own loop on weights doctored so that the
+    branch fires (oracle/eos_fixture.py; fixture made by oracle/pin_against_reference.py --only-eos from the unmodified modules)."""
+    from oracle import eos_fixture as EF
+    g = np.load(golden_dir / "eos_tiny.npz")
+    a = synthetic.ARCHS["tiny"]
+    sd = EF.doctor(synthetic.make_state_dict(a, seed=int(g["seed"])), a.gpt_dim)
+    n_new, n_rows = int(g["max_new_tokens"]), int(g["n_rows"])
+    prefix = EF.prefixes(n_rows, a.prefix_len, a.gpt_dim)
+    ids, lens, logits = O.greedy_decode(sd, prefix, torch.tensor([[EF.PROMPT]]), n_new, heads=a.gpt_heads, keep_logits=True)
+    assert lens.tolist() == g["lengths"].tolist()
+    assert ids.tolist() == g["ids"].tolist()
+    assert set(lens.tolist()) >= {1, n_new}                                   # rows that stop at step 0 and rows that never stop
+    assert all(ids[r, int(lens[r]):].eq(EF.EOS).all() for r in range(n_rows))  # later slots stay eos
+    m = torch.stack([EF.eos_margin(l) for l in logits], 0)
+    assert torch.allclose(m, torch.from_numpy(g["eos_margin"])[: m.shape[0]], atol=2e-3)
+    # a batch in which every row finishes at step 0: the loop ends after one forward (:224)
+    first = g["first_rows"].tolist()
+    ids1, lens1, lg1 = O.greedy_decode(sd, prefix[first], torch.tensor([[EF.PROMPT]]), n_new, heads=a.gpt_heads, keep_logits=True)
+    assert len(lg1) == int(g["first_steps_run"]) == 1
+    assert ids1.tolist() == g["first_ids"].tolist() and lens1.tolist() == g["first_lengths"].tolist()
+    # teacher forcing: feeding the trigger token makes the NEXT argmax eos, at any step we choose
+    forced = torch.randint(100, 40000, (n_rows, n_new), generator=torch.Generator().manual_seed(3))
+    live = [r for r in range(n_rows) if lens[r] == n_new][:3]
+    for r, s in zip(live, (0, 2, 6)):
+        forced[r, s] = EF.TRIGGER
+    ids_f, lens_f, _ = O.greedy_decode(sd, prefix, torch.tensor([[EF.PROMPT]]), n_new, heads=a.gpt_heads, forced_ids=forced)
+    assert [int(lens_f[r]) for r in live] == [2, 4, 8]

@@ -8,7 +8,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import vcb200  # noqa: F401
-from vcb200.sharding import gather_ids, shard_range
+from vcb200.sharding import IdGatherer, gather_ids, shard_range
 
 
 def test_shard_range_covers_all_videos_once():
@@ -37,6 +37,15 @@ def _worker(rank, world, port, n_videos, max_new, q):
     ids = torch.stack([_fake_ids(v, max_new) for v in range(lo, hi)]) if hi > lo else torch.zeros(0, max_new, dtype=torch.int32)
     lens = torch.tensor([(v % max_new) + 1 for v in range(lo, hi)], dtype=torch.int32)
     all_ids, all_len = gather_ids(ids, lens, n_videos)
+    # the preallocated single-collective gatherer bench.py uses: same global order, own block verified
+    per = (n_videos + world - 1) // world
+    g = IdGatherer(per, max_new, world, "cpu")
+    buf = g.gather(ids, lens)
+    assert g.check_own_block(buf, ids, lens, rank)
+    g_ids, g_len = g.global_order(buf, n_videos)
+    assert torch.equal(g_ids, all_ids) and torch.equal(g_len, all_len)
+    buf2 = g.gather(ids, lens)                          # reused buffers: a second batch gives the same answer
+    assert buf2.data_ptr() == buf.data_ptr() and g.check_own_block(buf2, ids, lens, rank)
     q.put((rank, all_ids.tolist(), all_len.tolist()))
     dist.barrier()
     dist.destroy_process_group()

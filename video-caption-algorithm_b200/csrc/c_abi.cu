@@ -74,7 +74,7 @@ static VitBuffers carve_vit(const VcVitWeights* w, int chunk_frames, void* base)
   b.delta2 = p + off;                       off += align_up(M * w->dim * 2, 1024);
   b.x_cls = reinterpret_cast<float*>(p + off); off += align_up(static_cast<size_t>(chunk_frames) * w->dim * 4, 1024);
   b.stats = reinterpret_cast<float*>(p + off); off += align_up(M * 8, 1024);                                     // (mean, rstd) per row
-  b.pstats = reinterpret_cast<float*>(p + off); off += align_up(M * 8 * 3 * ((w->dim + 255) / 256), 1024);      // partial (sum, sum sq)
+  b.pstats = reinterpret_cast<float*>(p + off); off += align_up(M * 8 * 4 * ((w->dim + 255) / 256), 1024);      // partial (sum, sum sq)
   b.total = off;
   return b;
 }
@@ -235,7 +235,7 @@ int vc_vit_encode(const VcVitWeights* w, const void* patches_bf16, int n_frames,
       // fc2 epilogues (x += bf16(acc + bias)); both emit bf16(x_new) — the A operand of the next product, whose weights
       // carry the LayerNorm affine (packing.fold_layernorm) — and partial row statistics; (mean, rstd) are applied in the
       // consumer's epilogue.  Only the first block's input needs a pass of its own (rows come from two producers).
-      const int parts = 3 * ((D + 255) / 256);
+      const int parts = 3 * ((D + 255) / 256);     // 3 epilogue warps per TMEM lane quarter and 256-column tile (gemm_tcgen05.cu)
       const int gelu_f = w->gelu_tanh ? VC_EPI_LNF_GELU_TANH : VC_EPI_LNF_GELU_ERF;
       if ((e = rowstats_cast(b.x, b.xn, b.stats, M, D, 1e-6f, s))) return e;
       for (int l = 0; l < w->layers; ++l) {

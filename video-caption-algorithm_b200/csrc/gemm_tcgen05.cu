@@ -47,7 +47,7 @@ constexpr int TMEM_COLS = 512;         // 2 accumulators x 256 fp32 columns
 // instruction-bound (ncu: the GELU epilogue executes 3x the instructions of the bias one and holds the tensor pipe at 68 %
 // active), so they get 16 warps = two 32-column chunks each; the residual + statistics epilogue waits on HBM, keeps a block
 // of residual values in flight per warp (128 registers), and stays at 12 warps (chunks 0-2, 3-5, 6-7).
-__host__ __device__ constexpr int epi_warps(int mode) { return mode == VC_EPI_RESID_STATS ? 12 : 16; }
+__host__ __device__ constexpr int epi_warps(int mode) { return mode == VC_EPI_RESID_STATS ? 12 : 16; }   // 16 x 112 registers does not launch
 constexpr int EPI_WARPS_MAX = 16;
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // one 32x32 fp32 block per warp
 __host__ __device__ constexpr int gemm_threads(int mode) { return (2 + epi_warps(mode)) * 32; }
@@ -382,7 +382,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
         // partial statistics of this warp's column chunks of this tile: slot (n tile, part) of the row
         if ((lane & 7) == 0 && n0 + c_begin * 32 < p.N) {
-          float2* ps = p.pstats + static_cast<size_t>((t % n_tiles) * 3 + part) * p.M;
+          float2* ps = p.pstats + static_cast<size_t>((t % n_tiles) * (EPI_WARPS / 4) + part) * p.M;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int row = row_base + i * 4 + (lane >> 3);
