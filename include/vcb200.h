@@ -190,6 +190,29 @@ int vc_beam_step(const float* logits, long long ld, int vocab, int n_rows, int r
 /* KV-cache beam reorder as an index update: slot_out[r][p] = slot_in[src_rows[r]][p] for p < upto */
 int vc_beam_reorder(const int32_t* slot_in, int32_t* slot_out, const int32_t* src_rows, int n_seq, int s_max, int upto, vc_stream_t stream);
 
+/* Beam bookkeeping of transformers `_beam_search` on the device (running / finished hypotheses, early-stop heuristic), one small
+ * kernel per step, so the whole beam loop is a fixed launch sequence (CUDA-graph capturable, no host round trip).  All arrays are
+ * caller-owned device memory.  Per step: vc_beam_step (scores + top 2*nb continuations) -> vc_beam_update -> vc_beam_reorder with
+ * src_rows -> next forward with next_tok.  After the last step: vc_beam_finalize. */
+typedef struct {
+  int32_t B, nb, max_len, eos;
+  float* running_scores;   /* [B, nb]            (the `running_scores` input of vc_beam_step) */
+  int32_t* running_seqs;   /* [B * nb, max_len]  (the `seqs` input of vc_beam_step) */
+  int32_t* fin_seqs;       /* [B, nb, max_len] */
+  float* fin_scores;       /* [B, nb] */
+  int32_t* fin_done;       /* [B, nb] */
+  int32_t* fin_len;        /* [B, nb] */
+  int32_t* unsatisfied;    /* [B] */
+  int32_t* flags;          /* [max_len + 1][2]: per step {some video unsatisfied, every candidate hit a stop} */
+  int32_t* stopped;        /* [1]: HF's loop would have ended (the finished pool is frozen from then on) */
+  int32_t* src_rows;       /* [B * nb] out: row each running beam continues from */
+  int32_t* next_tok;       /* [B * nb] out: token each running beam feeds next */
+} VcBeamState;
+int vc_beam_init(const VcBeamState* st, vc_stream_t stream);
+int vc_beam_update(const VcBeamState* st, const float* top_score, const int32_t* top_idx, int vocab, int cur_len, float length_penalty,
+                   vc_stream_t stream);
+int vc_beam_finalize(const VcBeamState* st, int32_t* ids_out /*[B,max_len] eos padded*/, int32_t* len_out /*[B]*/, vc_stream_t stream);
+
 /* ---- token selection on given logits (bit-exact vs torch.argmax / topk) ------------------- */
 int vc_argmax_f32(const float* logits, int rows, int vocab, int32_t* out, vc_stream_t stream);
 

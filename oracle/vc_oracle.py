@@ -351,12 +351,19 @@ def apply_processors(scores: torch.Tensor, seqs: torch.Tensor, cur_len: int, *, 
     return scores
 
 
-def sample_warpers(scores: torch.Tensor, temperature: float, top_p: float) -> torch.Tensor:
-    """do_sample=True branch of text_decoder.py:131-144: transformers TemperatureLogitsWarper (`scores / temperature`) then
-    TopPLogitsWarper (generation/logits_process.py: sort ascending, cumulative softmax, remove while cumsum <= 1 - top_p,
+def sample_warpers(scores: torch.Tensor, temperature: float, top_p: float, top_k: int = 50) -> torch.Tensor:
+    """do_sample=True branch of text_decoder.py:131-144: transformers TemperatureLogitsWarper (`scores / temperature`), then
+    TopKLogitsWarper — the reference passes no top_k, so GenerationConfig's default top_k = 50 is in force
+    (generation/utils.py `_get_logits_processor`: temperature, top_k, top_p in that order; logits_process.py: remove everything
+    below the k-th largest score) — then TopPLogitsWarper (sort ascending, cumulative softmax, remove while cumsum <= 1 - top_p,
     keep at least the last = most probable token, scatter the mask back, fill with -inf).  The draw itself
-    (`torch.multinomial`) uses the framework RNG and is not part of the oracle."""
+    (`torch.multinomial`) uses the framework RNG and is not part of the oracle.  Pinned against the installed transformers
+    classes by tests/test_oracle_golden.py::test_sample_warpers_equal_transformers_processors."""
     scores = scores / temperature
+    if top_k and top_k > 0:
+        k = min(int(top_k), scores.size(-1))
+        indices_to_remove = scores < torch.topk(scores, k)[0][..., -1, None]
+        scores = scores.masked_fill(indices_to_remove, float("-inf"))
     if top_p < 1.0:
         sorted_logits, sorted_indices = torch.sort(scores, descending=False)
         cumulative_probs = sorted_logits.softmax(dim=-1).cumsum(dim=-1)

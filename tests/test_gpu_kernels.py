@@ -364,3 +364,88 @@ def test_decode_chain_fused_fc_variant_matches(lib):
             os.environ.pop("VC_DECODE_FUSED_FC", None)
     assert (outs[0][1] - outs[1][1]).abs().max().item() < 2e-2
     assert (outs[0][0] == outs[1][0]).float().mean().item() >= 0.97      # only a near-tie may flip an argmax (different fp32 summation order)
+
+
+def test_beam_update_kernel_equals_torch_bookkeeping():
+    """vc_beam_update (one kernel per step) against the torch formulation of transformers' `_beam_search` state update
+    (_get_running_beams_for_next_iteration, _update_finished_beams, _check_early_stop_heuristic; the oracle's beam_search uses the
+    same lines), step by step on random candidate lists with eos hits, for 7 videos x 4 beams."""
+    import ctypes as C
+    from vcb200 import lib as L
+    lib = L.load()
+    B, nb, mx, V, eos = 7, 4, 12, 1000, 999
+    K = 2 * nb
+    NEG = -1.0e9
+    g = torch.Generator().manual_seed(0)
+    i32 = lambda *s: torch.zeros(*s, device=DEV, dtype=torch.int32)
+    f32 = lambda *s: torch.zeros(*s, device=DEV, dtype=torch.float32)
+    bufs = dict(running_scores=f32(B, nb), running_seqs=i32(B * nb, mx), fin_seqs=i32(B, nb, mx), fin_scores=f32(B, nb), fin_done=i32(B, nb),
+                fin_len=i32(B, nb), unsatisfied=i32(B), flags=i32(mx + 1, 2), stopped=i32(1), src_rows=i32(B * nb), next_tok=i32(B * nb))
+    bs = L.VcBeamState()
+    bs.B, bs.nb, bs.max_len, bs.eos = B, nb, mx, eos
+    for k, v in bufs.items():
+        setattr(bs, k, v.data_ptr())
+    st = torch.cuda.current_stream().cuda_stream
+    L.check(lib.vc_beam_init(C.byref(bs), st))
+    # torch reference state (CPU)
+    running_scores = torch.zeros(B, nb); running_scores[:, 1:] = NEG
+    running_seqs = torch.full((B, nb, mx), eos, dtype=torch.int64)
+    fin_seqs = running_seqs.clone(); fin_scores = torch.full((B, nb), NEG)
+    fin_done = torch.zeros(B, nb, dtype=torch.bool); fin_len = torch.zeros(B, nb, dtype=torch.int64)
+    unsat = torch.ones(B, 1, dtype=torch.bool); stopped = False
+    in_top = torch.arange(K).view(1, K) < nb
+    for cur_len in range(mx):
+        top_scores = torch.sort(torch.randn(B, K, generator=g) * 2 - 3 * (cur_len + 1), dim=1, descending=True).values
+        # candidates continue live beams only (a -1e9 filler beam can never reach the top 2*nb in a real search, and the order of
+        # fillers among themselves is not defined)
+        n_live = (running_scores > NEG / 2).sum(dim=1, keepdim=True).clamp(min=1)
+        top_beam = (torch.rand(B, K, generator=g) * n_live).floor().long().clamp(max=nb - 1)
+        top_tok = torch.randint(0, V - 1, (B, K), generator=g)
+        top_tok[torch.rand(B, K, generator=g) < (0.25 if cur_len >= 2 else 0.0)] = eos
+        top_idx = (top_beam * V + top_tok).int()
+        d_scores, d_idx = top_scores.to(DEV), top_idx.to(DEV)           # keep the device copies alive across the launch
+        L.check(lib.vc_beam_update(C.byref(bs), d_scores.data_ptr(), d_idx.data_ptr(), V, cur_len, 1.0, st))
+        torch.cuda.synchronize()
+        # ---- torch formulation
+        cand_seqs = torch.gather(running_seqs, 1, top_beam.unsqueeze(-1).expand(-1, -1, mx)).clone()
+        cand_seqs[:, :, cur_len] = top_tok
+        new_len = cur_len + 1
+        hit = (top_tok == eos) | (new_len >= mx)
+        run_rank = top_scores + hit.float() * NEG
+        running_scores, pick = torch.topk(run_rank, nb, dim=1)
+        running_seqs = torch.gather(cand_seqs, 1, pick.unsqueeze(-1).expand(-1, -1, mx))
+        running_beam, running_tok = torch.gather(top_beam, 1, pick), torch.gather(top_tok, 1, pick)
+        newly = hit & in_top
+        f = top_scores / (float(new_len) ** 1.0)
+        f = f + (~unsat).float() * NEG
+        f = f + (~newly).float() * NEG
+        ms, mseq = torch.cat([fin_scores, f], 1), torch.cat([fin_seqs, cand_seqs], 1)
+        md, ml = torch.cat([fin_done, newly], 1), torch.cat([fin_len, torch.full((B, K), new_len)], 1)
+        n_scores, sel = torch.topk(ms, nb, dim=1)
+        if not stopped:
+            fin_scores, fin_seqs = n_scores, torch.gather(mseq, 1, sel.unsqueeze(-1).expand(-1, -1, mx))
+            fin_done, fin_len = torch.gather(md, 1, sel), torch.gather(ml, 1, sel)
+        best_running = running_scores[:, :1] / (float(new_len) ** 1.0)
+        worst = torch.where(fin_done, fin_scores.min(dim=1, keepdim=True).values, torch.full_like(fin_scores, NEG))
+        unsat = unsat & (best_running > worst).any(dim=-1, keepdim=True)
+        stop_next = stopped or not (bool(unsat.any()) and not bool(hit.all()))
+        # ---- compare (valid entries only: ties among -1e9 fillers have no defined order)
+        ok_run = running_scores > NEG / 2
+        assert torch.equal(bufs["running_scores"].cpu()[ok_run], running_scores[ok_run]), cur_len
+        got_seqs = bufs["running_seqs"].cpu().view(B, nb, mx).long()
+        assert torch.equal(got_seqs[ok_run], running_seqs[ok_run]), cur_len
+        assert torch.equal(bufs["src_rows"].cpu().view(B, nb)[ok_run].long(), (running_beam + torch.arange(B).view(B, 1) * nb)[ok_run]), cur_len
+        assert torch.equal(bufs["next_tok"].cpu().view(B, nb)[ok_run].long(), running_tok[ok_run]), cur_len
+        ok_fin = fin_scores > NEG / 2
+        assert torch.equal(bufs["fin_scores"].cpu()[ok_fin], fin_scores[ok_fin]), cur_len
+        assert torch.equal(bufs["fin_seqs"].cpu().long()[ok_fin], fin_seqs[ok_fin]), cur_len
+        assert torch.equal(bufs["fin_done"].cpu().bool()[ok_fin], fin_done[ok_fin]) and torch.equal(bufs["fin_len"].cpu().long()[ok_fin], fin_len[ok_fin]), cur_len
+        assert torch.equal(bufs["unsatisfied"].cpu().bool().view(B, 1), unsat), cur_len
+        stopped = stop_next
+    ids = i32(B, mx); lens = i32(B)
+    L.check(lib.vc_beam_finalize(C.byref(bs), ids.data_ptr(), lens.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert lens.cpu().long().tolist() == fin_len[:, 0].tolist()
+    for b in range(B):
+        n = int(fin_len[b, 0])
+        assert ids[b, :n].cpu().long().tolist() == fin_seqs[b, 0, :n].tolist() and ids[b, n:].eq(eos).all()

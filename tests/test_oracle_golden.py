@@ -112,3 +112,22 @@ def test_eos_branch_matches_reference_loop(golden_dir):
         forced[r, s] = EF.TRIGGER
     ids_f, lens_f, _ = O.greedy_decode(sd, prefix, torch.tensor([[EF.PROMPT]]), n_new, heads=a.gpt_heads, forced_ids=forced)
     assert [int(lens_f[r]) for r in live] == [2, 4, 8]
+
+
+def test_sample_warpers_equal_transformers_processors():
+    """The sampling presets (core/inference.py "natural" / "safe_sample" -> generate(do_sample=True, temperature, top_p), default
+    top_k = 50): the oracle's warper chain equals the installed transformers classes in the order generate() builds them."""
+    from transformers.generation.logits_process import TemperatureLogitsWarper, TopKLogitsWarper, TopPLogitsWarper
+    # the reference pins transformers==4.57.1 (requirements.txt:38), whose GenerationConfig defaults to top_k = 50; the
+    # transformers 5.x installed here defaults to None, so the default is stated here rather than read from the installed package
+    g = torch.Generator().manual_seed(1)
+    scores = torch.randn(5, 50257, generator=g) * 3
+    ids = torch.zeros(5, 1, dtype=torch.long)
+    for temp, top_p in ((0.9, 0.9), (0.7, 0.95), (1.3, 0.5)):
+        want = scores.clone()
+        for proc in (TemperatureLogitsWarper(temp), TopKLogitsWarper(top_k=50, min_tokens_to_keep=1), TopPLogitsWarper(top_p=top_p, min_tokens_to_keep=1)):
+            want = proc(ids, want)
+        got = O.sample_warpers(scores.clone(), temp, top_p)
+        assert torch.equal(torch.isinf(got), torch.isinf(want))
+        assert torch.equal(got[~torch.isinf(got)], want[~torch.isinf(want)])
+        assert int((~torch.isinf(got)).sum(dim=-1).max()) <= 50

@@ -7,9 +7,9 @@ scores + the top-2*num_beams continuation search (`vc_beam_step`), and the KV-ca
 reorder as a slot-table update (`vc_beam_reorder`) instead of HF's per-layer index_select.
 The bookkeeping over B x 2*num_beams candidates per step (transformers
 `_get_running_beams_for_next_iteration`, `_update_finished_beams`, `_check_early_stop_heuristic`,
-SURVEY.md A.4) is a few hundred scalars: it stays in device tensors and is updated by small torch ops
-on the same stream, so a step has no host round trip (HF's own loop synchronises every step); the
-host reads the termination flag every fourth step.
+SURVEY.md A.4) is one small kernel per step (`vc_beam_update`), so the whole search is a fixed
+sequence of launches captured as a CUDA graph: no torch op and no host round trip per step (HF's own
+loop synchronises every step).
 
 The prefill runs ONCE per video (B rows); the num_beams-fold replication HF performs is
 expressed through the slot table (every beam of a video reads the prompt positions from the
@@ -33,124 +33,123 @@ NEG = -1.0e9
 def beam_search_ids(m, prefix: torch.Tensor, prompt_ids: List[int], *, max_new_tokens: int, num_beams: int,
                     no_repeat_ngram_size: int = 3, repetition_penalty: float = 1.1, min_new_tokens: int = 8,
                     length_penalty: float = 1.0, eos: int = EOS, do_sample: bool = False, temperature: float = 1.0, top_p: float = 1.0,
-                    generator=None):
+                    top_k: int = 50, generator=None, use_graph: bool = True):
     if num_beams == 1:
         return _greedy_with_processors(m, prefix, prompt_ids, max_new_tokens, no_repeat_ngram_size, repetition_penalty,
-                                       min_new_tokens, eos, do_sample=do_sample, temperature=temperature, top_p=top_p, generator=generator)
-    d = m.dims
-    dev = m.device
+                                       min_new_tokens, eos, do_sample=do_sample, temperature=temperature, top_p=top_p, top_k=top_k,
+                                       generator=generator)
+    with torch.cuda.device(m.device):
+        return _beam_search_device(m, prefix, prompt_ids, max_new_tokens, num_beams, int(no_repeat_ngram_size), float(repetition_penalty),
+                                   int(min_new_tokens), float(length_penalty), int(eos), use_graph)
+
+
+def _beam_state(m, B: int, P: int, Lp: int, nb: int, max_new: int, eos: int):
+    """Every buffer of one beam-search shape, allocated once and kept (m._graphs): KV cache with two slot tables, workspace,
+    logits, candidate buffers, the VcBeamState arrays, static input / output tensors and the captured graphs."""
+    d, dev = m.dims, m.device
+    key = ("beam", B, P, Lp, nb, max_new, eos)
+    st = m._graphs.get(key)
+    if st is not None:
+        return st
+    lib = L.load()
+    H, ld = d["gpt_dim"], d["vocab_pad"]
+    n_rows, K, L0 = B * nb, 2 * nb, P + Lp
+    s_max = L0 + max_new
+    cache = KvCache(d["gpt_layers"], n_rows, d["gpt_heads"], s_max, 64, dev, with_slots=True)
+    i32 = lambda *shape: torch.zeros(*shape, device=dev, dtype=torch.int32)
+    f32 = lambda *shape: torch.zeros(*shape, device=dev, dtype=torch.float32)
+    st = dict(cache=cache, slot_a=cache.slot, slot_b=cache.slot.clone(), slot_init=None,
+              ws=torch.empty(lib.vc_gpt_workspace_bytes(C.byref(m.packed.gpt), n_rows, max(n_rows, B * L0)), device=dev, dtype=torch.uint8),
+              logits=f32(n_rows, ld), embeds=f32(n_rows, H), x0=f32(B, L0, H), prompt=i32(max(Lp, 1)), tok_emb=f32(max(Lp, 1), H),
+              cand_score=f32(n_rows, K), cand_tok=i32(n_rows, K), top_score=f32(B, K), top_idx=i32(B, K), zeros=f32(n_rows),
+              running_scores=f32(B, nb), running_seqs=i32(n_rows, max_new), fin_seqs=i32(B, nb, max_new), fin_scores=f32(B, nb),
+              fin_done=i32(B, nb), fin_len=i32(B, nb), unsatisfied=i32(B), flags=i32(max_new + 1, 2), stopped=i32(1),
+              src_rows=i32(n_rows), next_tok=i32(n_rows), ids=i32(B, max_new), lens=i32(B), graphs={}, prompt_host=None)
+    # every beam row of video b reads the prompt positions from physical row b (prefilled once); decode positions follow the beam
+    init = torch.arange(n_rows, device=dev, dtype=torch.int32).view(n_rows, 1).repeat(1, s_max)
+    init[:, :L0] = (torch.arange(n_rows, device=dev, dtype=torch.int32) // nb).view(n_rows, 1)
+    st["slot_init"] = init.contiguous()
+    bs = L.VcBeamState()
+    bs.B, bs.nb, bs.max_len, bs.eos = B, nb, max_new, eos
+    for name in ("running_scores", "running_seqs", "fin_seqs", "fin_scores", "fin_done", "fin_len", "unsatisfied", "flags", "stopped",
+                 "src_rows", "next_tok"):
+        setattr(bs, name, st[name].data_ptr())
+    st["bs"] = bs
+    m._graphs[key] = st
+    return st
+
+
+def _beam_search_device(m, prefix, prompt_ids, max_new_tokens, nb, ngram, rep_penalty, min_new, length_penalty, eos, use_graph):
+    """transformers `_beam_search` as a FIXED sequence of launches: prefill once per video, then per step
+    vc_beam_step (log-softmax, processors, top 2*nb continuations) -> vc_beam_update (running / finished hypotheses, early-stop
+    heuristic) -> vc_beam_reorder (slot-table update) -> wte gather -> forward over B*nb rows.  No torch op and no host read inside
+    the loop, so the whole search is captured once per shape as a CUDA graph and replayed.  HF leaves its loop as soon as the
+    early-stop heuristic is satisfied; here the remaining steps still run but the finished pool is frozen from that step on
+    (VcBeamState.stopped), so the result is the same."""
+    d, dev = m.dims, m.device
     lib = L.load()
     gpt = C.byref(m.packed.gpt)
     B, P, H = prefix.shape
-    nb, V, ld = num_beams, d["vocab"], d["vocab_pad"]
-    K = 2 * nb
-    n_rows = B * nb
-    Lp = len(prompt_ids)
+    V, ld = d["vocab"], d["vocab_pad"]
+    K, n_rows, Lp = 2 * nb, B * nb, len(prompt_ids)
     L0 = P + Lp
     s_max = L0 + max_new_tokens
-    st = L.current_stream
+    st = _beam_state(m, B, P, Lp, nb, max_new_tokens, eos)
+    if st["prompt_host"] != tuple(prompt_ids):
+        st["prompt"][:Lp].copy_(torch.tensor(prompt_ids, dtype=torch.int32))
+        st["prompt_host"] = tuple(prompt_ids)
+    st["x0"][:, :P].copy_(prefix.to(device=dev, dtype=torch.float32))
+    stream = lambda: L.current_stream(dev)
+    bs = C.byref(st["bs"])
 
-    cache = KvCache(d["gpt_layers"], n_rows, d["gpt_heads"], s_max, 64, dev, with_slots=True)
-    # every beam row of video b reads the prompt positions from physical row b (prefilled once)
-    slot_a = cache.slot
-    slot_a[:, :L0] = (torch.arange(n_rows, device=dev, dtype=torch.int32) // nb).view(n_rows, 1)
-    slot_b = slot_a.clone()
-    ws = torch.empty(lib.vc_gpt_workspace_bytes(gpt, n_rows, max(n_rows, B * L0)), device=dev, dtype=torch.uint8)
-    logits = torch.empty(n_rows, ld, device=dev, dtype=torch.float32)
-    embeds = torch.empty(n_rows, H, device=dev, dtype=torch.float32)
-    cand_score = torch.empty(n_rows, K, device=dev, dtype=torch.float32)
-    cand_tok = torch.empty(n_rows, K, device=dev, dtype=torch.int32)
-    top_score = torch.empty(B, K, device=dev, dtype=torch.float32)
-    top_idx = torch.empty(B, K, device=dev, dtype=torch.int32)
-    seqs_dev = torch.full((n_rows, max_new_tokens), eos, device=dev, dtype=torch.int32)
-    run_dev = torch.zeros(n_rows, device=dev, dtype=torch.float32)
-    tok_dev = torch.empty(n_rows, device=dev, dtype=torch.int32)
-    src_dev = torch.empty(n_rows, device=dev, dtype=torch.int32)
+    def enqueue():
+        cache = st["cache"]
+        slot_a, slot_b = st["slot_a"], st["slot_b"]
+        # BOTH tables start from the initial mapping on every run: a reorder only rewrites positions below `past`, so the entry of
+        # the position a step is about to write must still say "own row" — it would hold the previous run's beam otherwise
+        slot_a.copy_(st["slot_init"])
+        slot_b.copy_(st["slot_init"])
+        cache.c.slot = slot_a.data_ptr()
+        L.check(lib.vc_beam_init(bs, stream()))
+        L.check(lib.vc_gpt2_embed_tokens(gpt, st["prompt"].data_ptr(), Lp, st["tok_emb"].data_ptr(), stream()))
+        st["x0"][:, P:].copy_(st["tok_emb"][:Lp].unsqueeze(0).expand(B, -1, -1))
+        L.check(lib.vc_gpt2_forward(gpt, st["x0"].data_ptr(), B, L0, 0, C.byref(cache.c), st["ws"].data_ptr(), st["ws"].numel(),
+                                    st["logits"].data_ptr(), 0, stream()))
+        for cur_len in range(max_new_tokens):
+            first = cur_len == 0
+            rows, per_item = (B, 1) if first else (n_rows, nb)
+            running = st["zeros"] if first else st["running_scores"]
+            L.check(lib.vc_beam_step(st["logits"].data_ptr(), ld, V, rows, per_item, st["running_seqs"].data_ptr(), max_new_tokens, cur_len,
+                                     running.data_ptr(), rep_penalty, ngram, min_new, eos, 0, K, st["cand_score"].data_ptr(),
+                                     st["cand_tok"].data_ptr(), st["top_score"].data_ptr(), st["top_idx"].data_ptr(), stream()))
+            L.check(lib.vc_beam_update(bs, st["top_score"].data_ptr(), st["top_idx"].data_ptr(), V, cur_len, length_penalty, stream()))
+            if cur_len + 1 >= max_new_tokens:
+                break
+            past = L0 + cur_len
+            if not first:
+                # positions written by decode steps follow their beam; prompt positions keep the per-video mapping
+                L.check(lib.vc_beam_reorder(slot_a.data_ptr(), slot_b.data_ptr(), st["src_rows"].data_ptr(), n_rows, s_max, past, stream()))
+                slot_a, slot_b = slot_b, slot_a
+                cache.c.slot = slot_a.data_ptr()
+            L.check(lib.vc_gpt2_embed_tokens(gpt, st["next_tok"].data_ptr(), n_rows, st["embeds"].data_ptr(), stream()))
+            L.check(lib.vc_gpt2_forward(gpt, st["embeds"].data_ptr(), n_rows, 1, past, C.byref(cache.c), st["ws"].data_ptr(), st["ws"].numel(),
+                                        st["logits"].data_ptr(), 0, stream()))
+        L.check(lib.vc_beam_finalize(bs, st["ids"].data_ptr(), st["lens"].data_ptr(), stream()))
 
-    # ---- prefill: [prefix | wte(prompt)] for the B videos
-    prompt = torch.tensor(prompt_ids, device=dev, dtype=torch.int32)
-    tok_emb = torch.empty(Lp, H, device=dev, dtype=torch.float32)
-    L.check(lib.vc_gpt2_embed_tokens(gpt, prompt.data_ptr(), Lp, tok_emb.data_ptr(), st()))
-    x0 = torch.cat([prefix.to(device=dev, dtype=torch.float32), tok_emb.unsqueeze(0).expand(B, -1, -1)], dim=1).contiguous()
-    L.check(lib.vc_gpt2_forward(gpt, x0.data_ptr(), B, L0, 0, C.byref(cache.c), ws.data_ptr(), ws.numel(), logits.data_ptr(), 0, st()))
-
-    # ---- beam state ON THE DEVICE (transformers `_beam_search` variable names in comments): a few hundred scalars per
-    # step, updated with small torch ops on the same stream, so a step needs no host round trip.  The host looks at the
-    # termination flag every `check_every` steps; once the flag is up the finished-hypothesis state is frozen, so the
-    # steps that run past HF's stopping point change nothing.
-    check_every = 4
-    running_scores = torch.zeros(B, nb, device=dev)
-    running_scores[:, 1:] = NEG
-    running_seqs = torch.full((B, nb, max_new_tokens), eos, dtype=torch.int64, device=dev)
-    fin_seqs = running_seqs.clone()                                   # sequences
-    fin_scores = torch.full((B, nb), NEG, device=dev)                  # beam_scores
-    fin_done = torch.zeros(B, nb, dtype=torch.bool, device=dev)        # is_sent_finished
-    fin_len = torch.zeros(B, nb, dtype=torch.int64, device=dev)
-    unsatisfied = torch.ones(B, 1, dtype=torch.bool, device=dev)       # is_early_stop_heuristic_unsatisfied
-    in_top = (torch.arange(K, device=dev).view(1, K) < nb)             # top_num_beam_mask
-    row_base = (torch.arange(B, device=dev) * nb).view(B, 1)
-    stopped = torch.zeros((), dtype=torch.bool, device=dev)            # HF's loop would have ended before this step
-    cur_len = 0
-    while True:
-        first = cur_len == 0
-        rows, per_item = (B, 1) if first else (n_rows, nb)
-        L.check(lib.vc_beam_step(logits.data_ptr(), ld, V, rows, per_item, seqs_dev.data_ptr(), max_new_tokens, cur_len,
-                                 run_dev.data_ptr(), float(repetition_penalty), int(no_repeat_ngram_size), int(min_new_tokens), eos, 0,
-                                 K, cand_score.data_ptr(), cand_tok.data_ptr(), top_score.data_ptr(), top_idx.data_ptr(), st()))
-        top_scores = top_score
-        flat = top_idx.to(torch.int64)
-        top_beam, top_tok = flat // V, flat % V
-        cand_seqs = torch.gather(running_seqs, 1, top_beam.unsqueeze(-1).expand(-1, -1, max_new_tokens)).clone()
-        cand_seqs[:, :, cur_len] = top_tok
-        new_len = cur_len + 1
-        hit_stop = (top_tok == eos) | (new_len >= max_new_tokens)
-        run_rank = top_scores + hit_stop.float() * NEG
-        running_scores, pick = torch.topk(run_rank, nb, dim=1)
-        running_seqs = torch.gather(cand_seqs, 1, pick.unsqueeze(-1).expand(-1, -1, max_new_tokens))
-        running_beam = torch.gather(top_beam, 1, pick)
-        running_tok = torch.gather(top_tok, 1, pick)
-        newly = hit_stop & in_top
-        f_scores = top_scores / (float(new_len) ** length_penalty)
-        f_scores = f_scores + (~unsatisfied).float() * NEG
-        f_scores = f_scores + (~newly).float() * NEG
-        merged_scores = torch.cat([fin_scores, f_scores], dim=1)
-        merged_seqs = torch.cat([fin_seqs, cand_seqs], dim=1)
-        merged_done = torch.cat([fin_done, newly], dim=1)
-        merged_len = torch.cat([fin_len, torch.full((B, K), new_len, dtype=torch.int64, device=dev)], dim=1)
-        n_scores, sel = torch.topk(merged_scores, nb, dim=1)
-        n_seqs = torch.gather(merged_seqs, 1, sel.unsqueeze(-1).expand(-1, -1, max_new_tokens))
-        n_done = torch.gather(merged_done, 1, sel)
-        n_len = torch.gather(merged_len, 1, sel)
-        # freeze the finished state once HF's loop would have stopped
-        fin_scores = torch.where(stopped, fin_scores, n_scores)
-        fin_seqs = torch.where(stopped, fin_seqs, n_seqs)
-        fin_done = torch.where(stopped, fin_done, n_done)
-        fin_len = torch.where(stopped, fin_len, n_len)
-        cur_len = new_len
-        best_running = running_scores[:, :1] / (float(cur_len) ** length_penalty)
-        worst_fin = torch.where(fin_done, fin_scores.min(dim=1, keepdim=True).values, torch.full_like(fin_scores, NEG))
-        unsatisfied = unsatisfied & (best_running > worst_fin).any(dim=-1, keepdim=True)
-        stopped = stopped | ~(unsatisfied.any() & ~hit_stop.all())
-        if cur_len >= max_new_tokens or (cur_len % check_every == 0 and bool(stopped)):      # the only host sync: every 4th step
-            break
-        # ---- next forward: reorder the cache by index, feed the chosen tokens
-        src_dev.copy_((running_beam + row_base).reshape(-1))
-        tok_dev.copy_(running_tok.reshape(-1))
-        seqs_dev.copy_(running_seqs.reshape(n_rows, max_new_tokens))
-        run_dev.copy_(running_scores.reshape(-1))
-        past = L0 + cur_len - 1
-        if not first:
-            # positions written by decode steps follow their beam; prompt positions keep the per-video mapping
-            L.check(lib.vc_beam_reorder(slot_a.data_ptr(), slot_b.data_ptr(), src_dev.data_ptr(), n_rows, s_max, past, st()))
-            slot_a, slot_b = slot_b, slot_a
-            cache.c.slot = slot_a.data_ptr()
-        L.check(lib.vc_gpt2_embed_tokens(gpt, tok_dev.data_ptr(), n_rows, embeds.data_ptr(), st()))
-        L.check(lib.vc_gpt2_forward(gpt, embeds.data_ptr(), n_rows, 1, past, C.byref(cache.c), ws.data_ptr(), ws.numel(),
-                                    logits.data_ptr(), 0, st()))
-    lengths = fin_len[:, 0].to(torch.int32)
-    pos = torch.arange(max_new_tokens, device=dev).view(1, -1)
-    ids = torch.where(pos < lengths.view(-1, 1), fin_seqs[:, 0, :], torch.full_like(fin_seqs[:, 0, :], eos)).to(torch.int32)
-    return ids, lengths
+    gkey = (ngram, rep_penalty, min_new, length_penalty)
+    if not use_graph:
+        enqueue()
+    elif gkey not in st["graphs"]:
+        enqueue()                                   # eager warm-up: func attributes are set outside the capture
+        torch.cuda.current_stream(dev).synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=torch.cuda.Stream(device=dev)):
+            enqueue()
+        st["graphs"][gkey] = g
+        g.replay()
+    else:
+        st["graphs"][gkey].replay()
+    return st["ids"].clone(), st["lens"].clone()           # the graph's static outputs are reused by the next call of this shape
 
 
 def _processed_scores(logits: torch.Tensor, seqs: torch.Tensor, cur_len: int, V: int, ngram: int, rep_penalty: float, min_new: int,
@@ -182,10 +181,17 @@ def _processed_scores(logits: torch.Tensor, seqs: torch.Tensor, cur_len: int, V:
     return scores
 
 
-def _warped_scores(scores: torch.Tensor, temperature: float, top_p: float) -> torch.Tensor:
-    """transformers TemperatureLogitsWarper then TopPLogitsWarper (min_tokens_to_keep=1): ascending sort, drop the tokens whose
-    cumulative probability stays <= 1 - top_p, always keep the most probable one."""
+def _warped_scores(scores: torch.Tensor, temperature: float, top_p: float, top_k: int = 50) -> torch.Tensor:
+    """transformers TemperatureLogitsWarper -> TopKLogitsWarper -> TopPLogitsWarper, the order `_get_logits_processor` builds them
+    in.  The reference calls `generate(do_sample=True, temperature, top_p)` without a top_k, so GenerationConfig's default
+    top_k = 50 applies (text_decoder.py:131-144): everything below the 50th largest score is masked before the nucleus is cut.
+    Top-p (min_tokens_to_keep=1): ascending sort, drop the tokens whose cumulative probability stays <= 1 - top_p, always keep
+    the most probable one."""
     scores = scores / torch.full_like(scores[:, :1], float(temperature))
+    if top_k and top_k > 0:
+        k = min(int(top_k), scores.shape[-1])
+        kth = torch.topk(scores, k, dim=-1).values[:, -1:]
+        scores = scores.masked_fill(scores < kth, float("-inf"))
     if top_p < 1.0:
         srt, idx = torch.sort(scores, descending=False, dim=-1)
         remove = srt.softmax(dim=-1).cumsum(dim=-1) <= (1.0 - float(top_p))
@@ -195,7 +201,7 @@ def _warped_scores(scores: torch.Tensor, temperature: float, top_p: float) -> to
 
 
 def _greedy_with_processors(m, prefix, prompt_ids, max_new_tokens, ngram, rep_penalty, min_new, eos, *, do_sample: bool = False,
-                            temperature: float = 1.0, top_p: float = 1.0, generator=None):
+                            temperature: float = 1.0, top_p: float = 1.0, top_k: int = 50, generator=None):
     """HF `_sample`: processors on the raw last-position logits, then argmax (do_sample=False) or temperature / top-p warpers,
     softmax and `torch.multinomial` (do_sample=True: text_decoder.py:137, presets "natural" / "safe_sample"); finished rows
     emit pad(=eos); stop when every row has produced eos or at max_new_tokens.  All state stays on the device: the host reads
@@ -209,7 +215,7 @@ def _greedy_with_processors(m, prefix, prompt_ids, max_new_tokens, ngram, rep_pe
     V, ld = d["vocab"], d["vocab_pad"]
     Lp = len(prompt_ids)
     L0 = P + Lp
-    st = L.current_stream
+    st = lambda: L.current_stream(dev)
     cache = KvCache(d["gpt_layers"], B, d["gpt_heads"], L0 + max_new_tokens, 64, dev)
     ws = torch.empty(lib.vc_gpt_workspace_bytes(gpt, B, B * L0), device=dev, dtype=torch.uint8)
     logits = torch.empty(B, ld, device=dev, dtype=torch.float32)
@@ -231,7 +237,7 @@ def _greedy_with_processors(m, prefix, prompt_ids, max_new_tokens, ngram, rep_pe
     for cur_len in range(max_new_tokens):
         if do_sample:
             scores = _processed_scores(logits, seqs_dev, cur_len, V, int(ngram), float(rep_penalty), int(min_new), eos)
-            scores = _warped_scores(scores, temperature, top_p)
+            scores = _warped_scores(scores, temperature, top_p, top_k)
             nxt = torch.multinomial(scores.softmax(dim=-1), 1, generator=generator).view(-1).to(torch.int32)
         else:
             L.check(lib.vc_beam_step(logits.data_ptr(), ld, V, B, 1, seqs_dev.data_ptr(), max_new_tokens, cur_len, 0, float(rep_penalty),

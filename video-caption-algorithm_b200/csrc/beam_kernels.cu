@@ -4,9 +4,13 @@
 // scores and the top-2*num_beams continuation search over num_beams * vocab candidates
 // (`_get_top_k_continuations`), plus the KV-cache beam reorder as a slot-table update
 // instead of HF's `index_select` copy of every layer's K/V.
-// The tiny per-step bookkeeping over B x 2*num_beams candidates stays on the host (beam.py).
+// The per-step bookkeeping over B x 2*num_beams candidates (running / finished hypotheses, early-stop heuristic) is one small
+// kernel per step (beam_update_kernel), so the whole beam loop is a fixed sequence of launches: CUDA-graph capturable.
 #include "vc_common.cuh"
 #include "vc_kernels.h"
+
+#include <algorithm>
+#include <cmath>
 
 namespace vc {
 
@@ -170,7 +174,168 @@ __global__ void beam_reorder_kernel(const int32_t* __restrict__ slot_in, int32_t
   slot_out[r * s_max + p] = slot_in[src[r] * s_max + p];
 }
 
+// ---------------------------------------------------------------------------------------------- beam bookkeeping
+// transformers `_beam_search` per-step state update (installed generation/utils.py: _get_running_beams_for_next_iteration,
+// _update_finished_beams, _check_early_stop_heuristic, _beam_search_has_unfinished_sequences) for ONE video per
+// CTA (32 threads; lane k = candidate k of the top 2*num_beams).  Arithmetic mirrors the torch formulation op for op
+// (score + stop * -1e9, score / len**lp + ... ), selection is top-n by (value descending, index ascending).
+constexpr float BM_NEG = -1.0e9f;
+constexpr int BM_MAX_LEN = 256;
+
+__device__ __forceinline__ int rank_among(float v, int self, int n, bool valid) {
+  // position of (v, self) in the descending order of the n values held by lanes 0..n-1 (ties: lower lane first)
+  int r = 0;
+  for (int j = 0; j < n; ++j) {
+    const float vj = __shfl_sync(0xffffffffu, v, j);
+    r += (vj > v || (vj == v && j < self)) ? 1 : 0;
+  }
+  return valid ? r : 0x7fffffff;
+}
+
+__global__ void __launch_bounds__(32) beam_update_kernel(VcBeamState st, const float* __restrict__ top_score, const int32_t* __restrict__ top_idx,
+                                                         int vocab, int cur_len, float den) {
+  __shared__ int32_t s_run[16][BM_MAX_LEN], s_fin[16][BM_MAX_LEN];
+  __shared__ int s_pick[16], s_pbeam[16], s_ptok[16], s_sel[16], s_sbeam[16], s_stok[16];
+  __shared__ float s_fs[16];
+  __shared__ int s_fd[16];
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int nb = st.nb, K = 2 * nb, L = st.max_len;
+  const int new_len = cur_len + 1;
+  // has HF's loop already ended?  (evaluated from the flags the PREVIOUS step's CTAs left; sticky)
+  int stopped = *st.stopped;
+  if (cur_len > 0) {
+    const int any_unsat = st.flags[2 * (cur_len - 1)], all_hit = st.flags[2 * (cur_len - 1) + 1];
+    stopped |= !(any_unsat != 0 && all_hit == 0);
+  }
+  for (int i = lane; i < nb * L; i += 32) {
+    s_run[i / L][i % L] = st.running_seqs[static_cast<long long>(b) * nb * L + i];
+    s_fin[i / L][i % L] = st.fin_seqs[static_cast<long long>(b) * nb * L + i];
+  }
+  const bool cand = lane < K;
+  const float score = cand ? top_score[b * K + lane] : -INFINITY;
+  const int flat = cand ? top_idx[b * K + lane] : 0;
+  const int beam = flat / vocab, tok = flat - beam * vocab;
+  const bool hit = cand && (tok == st.eos || new_len >= L);
+  __syncwarp();
+  // ---- running beams of the next iteration: top nb of (score, stopped candidates pushed down by -1e9)
+  const float run_v = score + (hit ? 1.f : 0.f) * BM_NEG;
+  const int r_run = rank_among(run_v, lane, K, cand);
+  if (r_run < nb) {
+    s_pick[r_run] = lane; s_pbeam[r_run] = beam; s_ptok[r_run] = tok;
+    st.running_scores[b * nb + r_run] = run_v;
+    st.src_rows[b * nb + r_run] = b * nb + beam;
+    st.next_tok[b * nb + r_run] = tok;
+  }
+  // ---- finished pool: candidates in the first nb slots that just stopped, merged with the pool, top nb by normalised score
+  const int unsat = st.unsatisfied[b];
+  const bool newly = hit && lane < nb;
+  float f = score / den;
+  f = f + (unsat ? 0.f : 1.f) * BM_NEG;
+  f = f + (newly ? 0.f : 1.f) * BM_NEG;
+  // merged order: lanes 0..nb-1 = pool entries, lanes nb..nb+K-1 = candidates  (torch.cat([fin, cand]))
+  const float pool_v = lane < nb ? st.fin_scores[b * nb + lane] : -INFINITY;
+  const float cand_f = __shfl_sync(0xffffffffu, f, lane >= nb ? lane - nb : 0);
+  const bool m_valid = lane < nb + K;
+  const float m_v = lane < nb ? pool_v : (m_valid ? cand_f : -INFINITY);
+  const int r_fin = rank_among(m_v, lane, nb + K, m_valid);
+  const int pool_done = lane < nb ? st.fin_done[b * nb + lane] : 0;
+  const int pool_len = lane < nb ? st.fin_len[b * nb + lane] : 0;
+  const int c_newly = __shfl_sync(0xffffffffu, newly ? 1 : 0, lane >= nb ? lane - nb : 0);
+  const int c_beam = __shfl_sync(0xffffffffu, beam, lane >= nb ? lane - nb : 0), c_tok = __shfl_sync(0xffffffffu, tok, lane >= nb ? lane - nb : 0);
+  if (r_fin < nb) {
+    s_sel[r_fin] = lane; s_sbeam[r_fin] = c_beam; s_stok[r_fin] = c_tok;
+    s_fs[r_fin] = m_v;
+    s_fd[r_fin] = lane < nb ? pool_done : c_newly;
+  }
+  __syncwarp();
+  const int sel_len = (r_fin < nb) ? (lane < nb ? pool_len : new_len) : 0;
+  // ---- write the new running sequences (old sequence of the source beam + the chosen token)
+  for (int i = lane; i < nb * L; i += 32) {
+    const int r = i / L, p = i - r * L;
+    st.running_seqs[static_cast<long long>(b) * nb * L + i] = p == cur_len ? s_ptok[r] : s_run[s_pbeam[r]][p];
+  }
+  // ---- write the new finished pool unless HF's loop has already ended
+  if (!stopped) {
+    for (int i = lane; i < nb * L; i += 32) {
+      const int r = i / L, p = i - r * L;
+      const int src = s_sel[r];
+      st.fin_seqs[static_cast<long long>(b) * nb * L + i] = src < nb ? s_fin[src][p] : (p == cur_len ? s_stok[r] : s_run[s_sbeam[r]][p]);
+    }
+    if (r_fin < nb) {
+      st.fin_scores[b * nb + r_fin] = m_v;
+      st.fin_done[b * nb + r_fin] = s_fd[r_fin];
+      st.fin_len[b * nb + r_fin] = sel_len;
+    }
+  }
+  // ---- early-stop heuristic on the (possibly frozen) pool
+  float fs = 0.f; int fd = 0;
+  if (lane < nb) {
+    fs = stopped ? st.fin_scores[b * nb + lane] : s_fs[lane];
+    fd = stopped ? st.fin_done[b * nb + lane] : s_fd[lane];
+  }
+  float mn = lane < nb ? fs : INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  const float best_running = __shfl_sync(0xffffffffu, run_v, s_pick[0]) / den;
+  const bool gt = lane < nb && best_running > (fd ? mn : BM_NEG);
+  const unsigned any_gt = __ballot_sync(0xffffffffu, gt);
+  const int unsat_new = unsat && any_gt != 0;
+  const unsigned hits = __ballot_sync(0xffffffffu, hit);
+  if (lane == 0) {
+    st.unsatisfied[b] = unsat_new;
+    if (unsat_new) atomicOr(&st.flags[2 * cur_len], 1);
+    if (hits != ((K >= 32) ? 0xffffffffu : ((1u << K) - 1))) atomicAnd(&st.flags[2 * cur_len + 1], 0);
+    if (b == 0) *st.stopped = stopped;
+  }
+}
+
+__global__ void beam_init_kernel(VcBeamState st) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_rows = st.B * st.nb;
+  if (i < n_rows * st.max_len) { st.running_seqs[i] = st.eos; st.fin_seqs[i] = st.eos; }
+  if (i < n_rows) {
+    st.running_scores[i] = (i % st.nb) == 0 ? 0.f : BM_NEG;
+    st.fin_scores[i] = BM_NEG; st.fin_done[i] = 0; st.fin_len[i] = 0;
+  }
+  if (i < st.B) st.unsatisfied[i] = 1;
+  if (i <= st.max_len) { st.flags[2 * i] = 0; st.flags[2 * i + 1] = 1; }
+  if (i == 0) *st.stopped = 0;
+}
+
+// best finished hypothesis per video, cropped to its length, eos padded
+__global__ void beam_finalize_kernel(VcBeamState st, int32_t* __restrict__ ids_out, int32_t* __restrict__ len_out) {
+  const int b = blockIdx.x;
+  const int n = st.fin_len[b * st.nb];
+  for (int p = threadIdx.x; p < st.max_len; p += blockDim.x)
+    ids_out[b * st.max_len + p] = p < n ? st.fin_seqs[static_cast<long long>(b) * st.nb * st.max_len + p] : st.eos;
+  if (threadIdx.x == 0) len_out[b] = n;
+}
+
 }  // namespace
+
+int beam_init(const VcBeamState* st, cudaStream_t s) {
+  VC_REQUIRE(st != nullptr && st->nb >= 1 && st->nb <= 8 && st->max_len >= 1 && st->max_len <= BM_MAX_LEN && st->B >= 1,
+             "beam_init: B=%d nb=%d max_len=%d", st ? st->B : 0, st ? st->nb : 0, st ? st->max_len : 0);
+  const int total = std::max(st->B * st->nb * st->max_len, st->max_len + 1);
+  VC_LAUNCH("beam_init", 0.0, s, (beam_init_kernel<<<(total + 255) / 256, 256, 0, s>>>(*st)));
+  VC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int beam_update(const VcBeamState* st, const float* top_score, const int32_t* top_idx, int vocab, int cur_len, float length_penalty, cudaStream_t s) {
+  VC_REQUIRE(st != nullptr && st->nb >= 1 && st->nb <= 8 && st->max_len <= BM_MAX_LEN && cur_len >= 0 && cur_len < st->max_len,
+             "beam_update: nb=%d max_len=%d cur_len=%d", st ? st->nb : 0, st ? st->max_len : 0, cur_len);
+  const float den = static_cast<float>(std::pow(static_cast<double>(cur_len + 1), static_cast<double>(length_penalty)));
+  VC_LAUNCH("beam_update", 0.0, s, (beam_update_kernel<<<st->B, 32, 0, s>>>(*st, top_score, top_idx, vocab, cur_len, den)));
+  VC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int beam_finalize(const VcBeamState* st, int32_t* ids_out, int32_t* len_out, cudaStream_t s) {
+  VC_LAUNCH("beam_finalize", 0.0, s, (beam_finalize_kernel<<<st->B, 64, 0, s>>>(*st, ids_out, len_out)));
+  VC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 int beam_step(const float* logits, long long ld, int vocab, int n_rows, int rows_per_item, const int32_t* seqs, int max_len, int cur_len,
               const float* running, float rep_penalty, int ngram, int min_new, int eos, int raw, int K, float* cand_score,
@@ -180,10 +345,14 @@ int beam_step(const float* logits, long long ld, int vocab, int n_rows, int rows
   VC_REQUIRE(cur_len <= max_len && cur_len < BS_THREADS, "beam_step: cur_len=%d", cur_len);
   const int smem = vocab * static_cast<int>(sizeof(float));
   VC_REQUIRE(smem <= 220 * 1024, "beam_step: vocab=%d does not fit in shared memory", vocab);
-  static int attr = 0;
-  if (smem > attr) {
-    VC_CUDA_OK(cudaFuncSetAttribute(beam_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = smem;
+  {
+    static int attr[64] = {0};                 // per device: a second GPU in the same process needs its own opt-in
+    int dev = 0;
+    VC_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || smem > attr[dev]) {
+      VC_CUDA_OK(cudaFuncSetAttribute(beam_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      if (dev >= 0 && dev < 64) attr[dev] = smem;
+    }
   }
   VC_LAUNCH("beam_scores", static_cast<double>(n_rows) * vocab * 4.0, s,
             (beam_scores_kernel<<<n_rows, BS_THREADS, smem, s>>>(logits, ld, vocab, seqs, max_len, cur_len, running, rep_penalty, ngram,

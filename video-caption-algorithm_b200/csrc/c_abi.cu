@@ -36,7 +36,10 @@ static std::mutex g_prof_mu;
 
 KernelScope::KernelScope(const char* name, double work, cudaStream_t stream) : stream_(stream), slot_(-1) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  if (g_prof_on) {
+  // no timing events inside a stream capture: they would become graph nodes, and cudaEventElapsedTime on them fails later
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  const bool capturing = cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone;
+  if (g_prof_on && !capturing) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     ProfRec r{name, work, nullptr, nullptr};
     if (cudaEventCreate(&r.a) == cudaSuccess && cudaEventCreate(&r.b) == cudaSuccess) {
@@ -131,7 +134,7 @@ using namespace vc;
 extern "C" {
 
 const char* vc_last_error(void) { return g_err; }
-int vc_abi_version(void) { return 3; }
+int vc_abi_version(void) { return 4; }
 int vc_num_sms(void) {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
@@ -156,7 +159,7 @@ int vc_prof_end(int max_rows, char* names, float* total_ms, int* calls, double* 
   int n = 0;
   for (auto& r : g_prof) {
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, r.a, r.b);
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) { ms = 0.f; (void)cudaGetLastError(); }   // never leave an error behind
     auto it = index.find(r.name);
     int i;
     if (it == index.end()) {
@@ -454,6 +457,15 @@ int vc_beam_step(const float* logits, long long ld, int vocab, int n_rows, int r
                  int K, float* cand_score, int32_t* cand_tok, float* top_score, int32_t* top_idx, vc_stream_t stream) {
   return beam_step(logits, ld, vocab, n_rows, rows_per_item, seqs, max_len, cur_len, running_scores, repetition_penalty, no_repeat_ngram,
                    min_new_tokens, eos, raw_logits, K, cand_score, cand_tok, top_score, top_idx, S(stream));
+}
+
+int vc_beam_init(const VcBeamState* st, vc_stream_t stream) { return beam_init(st, S(stream)); }
+int vc_beam_update(const VcBeamState* st, const float* top_score, const int32_t* top_idx, int vocab, int cur_len, float length_penalty,
+                   vc_stream_t stream) {
+  return beam_update(st, top_score, top_idx, vocab, cur_len, length_penalty, S(stream));
+}
+int vc_beam_finalize(const VcBeamState* st, int32_t* ids_out, int32_t* len_out, vc_stream_t stream) {
+  return beam_finalize(st, ids_out, len_out, S(stream));
 }
 
 int vc_beam_reorder(const int32_t* slot_in, int32_t* slot_out, const int32_t* src_rows, int n_seq, int s_max, int upto, vc_stream_t stream) {

@@ -445,18 +445,17 @@ int make_map(CUtensorMap* tm, const void* ptr, int rows, int K, int box_rows) { 
 
 int g_num_sms = 0;
 std::mutex g_cfg_mu;
-bool g_attr_set[16] = {false};
+PerDeviceOnce g_attr_set[16];
 
 template <int MODE>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t stream) {
   {
     std::lock_guard<std::mutex> lk(g_cfg_mu);
-    if (!g_attr_set[MODE]) {
+    if (g_attr_set[MODE].first()) {
       VC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(MODE)));
       // ask for the largest shared-memory carve-out, not the smallest that holds SMEM_BYTES: what is left over (~45 KB)
       // is where the decode chain's CTAs of the previous batch run beside this kernel's resident CTAs (CaptionPipeline)
       VC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      g_attr_set[MODE] = true;
     }
   }
   static const char* const kNames[] = {"gemm_bias", "gemm_gelu_erf", "gemm_gelu_tanh", "gemm_resid", "gemm_f32", "gemm_patch",
@@ -503,10 +502,18 @@ int gemm_bf16_ex(const void* A, const void* W, const float* bias, int M, int N, 
                  (reinterpret_cast<uintptr_t>(out) & 15) == 0,
              "gemm: operands must be 16-byte aligned");
   VC_REQUIRE(get_encode() == 0, "gemm: cuTensorMapEncodeTiled entry point not found (no CUDA driver?)");
-  if (g_num_sms == 0) {
+  {
     int dev = 0;
     VC_CUDA_OK(cudaGetDevice(&dev));
-    VC_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    static int sms_of[64] = {0};
+    if (dev < 0 || dev >= 64 || sms_of[dev] == 0) {
+      int n = 0;
+      VC_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+      if (dev >= 0 && dev < 64) sms_of[dev] = n;
+      g_num_sms = n;
+    } else {
+      g_num_sms = sms_of[dev];
+    }
   }
   CUtensorMap ta, tb;
   if (int e = make_map(&ta, A, M, K, BM)) return e;

@@ -340,11 +340,8 @@ int skinny_gemm(const void* x, const void* W, float* P, int M, int N, int K, int
   const int kslice = K / ksplit;
   if (kslice <= SK_STAGE_MAX) {
     const size_t smem = static_cast<size_t>(SK_MT) * (kslice * 2 + 64);
-    static bool attr = false;
-    if (!attr) {
-      VC_CUDA_OK(cudaFuncSetAttribute(skinny_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_MT * (SK_STAGE_MAX * 2 + 64)));
-      attr = true;
-    }
+    static PerDeviceOnce attr;
+    if (attr.first()) VC_CUDA_OK(cudaFuncSetAttribute(skinny_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_MT * (SK_STAGE_MAX * 2 + 64)));
     VC_LAUNCH("skinny_gemm", static_cast<double>(N) * K * 2.0, s,
               VC_CUDA_OK(launch_pdl(skinny_gemm_kernel<true>, grid, dim3(SK_WARPS * 32), smem, s, static_cast<const __nv_bfloat16*>(x),
                                     static_cast<const __nv_bfloat16*>(W), P, M, N, K, kslice)));

@@ -19,6 +19,21 @@ struct KernelScope {
   int slot_;
 };
 
+// "Done once per device" flags for cudaFuncSetAttribute: the attribute lives per (function, device), so a second GPU in the same
+// process (InferenceConfig.device = "cuda:1") needs its own opt-in to > 48 KB of dynamic shared memory.
+struct PerDeviceOnce {
+  bool done[64] = {false};
+  // true if the caller still has to set the attribute on the current device (and marks it done)
+  bool first(int* dev_out = nullptr) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (dev_out) *dev_out = dev;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 // Launch with the programmatic-stream-serialization attribute (the kernel must begin with pdl_wait()).
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
@@ -133,6 +148,9 @@ int chain_set_trace(void* buf, int max_records);
 int beam_step(const float* logits, long long ld, int vocab, int n_rows, int rows_per_item, const int32_t* seqs, int max_len, int cur_len,
               const float* running, float rep_penalty, int ngram, int min_new, int eos, int raw, int K, float* cand_score,
               int32_t* cand_tok, float* top_score, int32_t* top_idx, cudaStream_t s);
+int beam_init(const VcBeamState* st, cudaStream_t s);
+int beam_update(const VcBeamState* st, const float* top_score, const int32_t* top_idx, int vocab, int cur_len, float length_penalty, cudaStream_t s);
+int beam_finalize(const VcBeamState* st, int32_t* ids_out, int32_t* len_out, cudaStream_t s);
 int beam_reorder(const int32_t* slot_in, int32_t* slot_out, const int32_t* src_rows, int n_seq, int s_max, int upto, cudaStream_t s);
 
 }  // namespace vc

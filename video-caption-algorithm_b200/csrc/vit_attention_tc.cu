@@ -349,7 +349,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 }
 
 int g_at_sms = 0;
-bool g_at_attr = false;
+PerDeviceOnce g_at_attr;
 
 }  // namespace
 
@@ -367,10 +367,7 @@ int vit_attention_tc(const void* qkv, void* out, int n_frames, int tokens, int h
     VC_CUDA_OK(cudaGetDevice(&dev));
     VC_CUDA_OK(cudaDeviceGetAttribute(&g_at_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  if (!g_at_attr) {
-    VC_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    g_at_attr = true;
-  }
+  if (g_at_attr.first()) VC_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
   CUtensorMap tq, tkv;
   const int rows = n_frames * tokens;
   int e;

@@ -524,11 +524,8 @@ int vit_attention_mma_sync(const void* qkv, void* out, int n_frames, int tokens,
   if (n_frames <= 0) return 0;
   const int s_pad = ((tokens + 63) / 64) * 64;
   const int smem = 3 * s_pad * 128;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    VC_CUDA_OK(cudaFuncSetAttribute(vit_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
-  }
+  static PerDeviceOnce attr;                    // opt in to the largest size this kernel ever needs (576 tokens), once per device
+  if (attr.first()) VC_CUDA_OK(cudaFuncSetAttribute(vit_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 576 * 128));
   const double flops = 4.0 * n_frames * heads * static_cast<double>(tokens) * tokens * HD;
   VC_LAUNCH("vit_attention", flops, s,
             (vit_attention_kernel<<<n_frames * heads, ATT_THREADS, smem, s>>>(static_cast<const __nv_bfloat16*>(qkv),

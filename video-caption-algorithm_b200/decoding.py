@@ -25,9 +25,10 @@ from .memory import KvCache
 EOS = 50256
 
 
-def _greedy_buffers(m, n_seq: int, L0: int, max_new: int, keep_logits: bool):
+def _greedy_buffers(m, n_seq: int, P: int, Lp: int, max_new: int, keep_logits: bool):
     d = m.dims
-    key = ("greedy", n_seq, L0, max_new, keep_logits)
+    L0 = P + Lp
+    key = ("greedy", n_seq, P, Lp, max_new, keep_logits)      # P and Lp are baked into the captured call, not only their sum
     st = m._graphs.get(key)
     if st is None:
         cache = KvCache(d["gpt_layers"], n_seq, d["gpt_heads"], L0 + max_new, 64, m.device)
@@ -53,12 +54,12 @@ def greedy_decode(m, prefix: torch.Tensor, prompt_ids: List[int], max_new: int, 
     n_seq, P, H = prefix.shape
     Lp = len(prompt_ids)
     L0 = P + Lp
-    st = _greedy_buffers(m, n_seq, L0, max_new, keep_logits)
+    st = _greedy_buffers(m, n_seq, P, Lp, max_new, keep_logits)
     pre = st["prefix"].view(-1)[: n_seq * P * H].view(n_seq, P, H)
     pre.copy_(prefix.to(device=m.device, dtype=torch.float32))
     if st.get("prompt_host") != tuple(prompt_ids):          # H2D of the prompt ids only when they change
         st["prompt"][:Lp].copy_(torch.tensor(prompt_ids, dtype=torch.int32), non_blocking=False)
-        torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream(m.device).synchronize()
         st["prompt_host"] = tuple(prompt_ids)
     use_forced = forced_ids is not None
     if use_forced:
@@ -69,14 +70,14 @@ def greedy_decode(m, prefix: torch.Tensor, prompt_ids: List[int], max_new: int, 
         L.check(lib.vc_greedy_decode(C.byref(m.packed.gpt), pre.data_ptr(), n_seq, P, st["prompt"].data_ptr(), Lp, max_new, EOS,
                                      C.byref(st["cache"].c), st["ws"].data_ptr(), st["ws"].numel(), st["ids"].data_ptr(),
                                      st["lens"].data_ptr(), st["forced"].data_ptr() if use_forced else 0,
-                                     st["logits"].data_ptr() if keep_logits else 0, L.current_stream()))
+                                     st["logits"].data_ptr() if keep_logits else 0, L.current_stream(m.device)))
 
     gkey = "graph_forced" if use_forced else "graph"
     if not use_graph:
         enqueue()
     elif st[gkey] is None:
         enqueue()                              # eager warm-up (also sets func attributes outside capture)
-        torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream(m.device).synchronize()
         g = torch.cuda.CUDAGraph()
         # kernel nodes keep the priority of the stream they were captured on (model.decode_priority: equal to the encoder's)
         cap = torch.cuda.Stream(device=m.device, priority=int(os.environ.get("VC_DECODE_PRIORITY", "0")))
@@ -92,9 +93,10 @@ def greedy_decode(m, prefix: torch.Tensor, prompt_ids: List[int], max_new: int, 
 
 def hf_generate_ids(m, prefix: torch.Tensor, prompt_ids: List[int], *, max_new_tokens: int, num_beams: int = 1,
                     no_repeat_ngram_size: int = 3, repetition_penalty: float = 1.1, min_new_tokens: int = 8,
-                    length_penalty: float = 1.0, do_sample: bool = False, temperature: float = 1.0, top_p: float = 1.0, generator=None):
+                    length_penalty: float = 1.0, do_sample: bool = False, temperature: float = 1.0, top_p: float = 1.0, top_k: int = 50,
+                    generator=None):
     from .beam import beam_search_ids
     return beam_search_ids(m, prefix, prompt_ids, max_new_tokens=max_new_tokens, num_beams=num_beams,
                            no_repeat_ngram_size=no_repeat_ngram_size, repetition_penalty=repetition_penalty,
                            min_new_tokens=min_new_tokens, length_penalty=length_penalty, do_sample=do_sample,
-                           temperature=temperature, top_p=top_p, generator=generator)
+                           temperature=temperature, top_p=top_p, top_k=top_k, generator=generator)

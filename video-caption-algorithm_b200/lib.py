@@ -21,7 +21,7 @@ HEADERS = ["vc_common.cuh", "vc_kernels.h", "../../include/vcb200.h"]
 # -cudart shared: the runtime is the process's libcudart.so (torch ships one), not a private static copy inside the library
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
-ABI_VERSION = 3          # == vc_abi_version(); bumped with every struct / signature change (include/vcb200.h)
+ABI_VERSION = 4          # == vc_abi_version(); bumped with every struct / signature change (include/vcb200.h)
 
 
 class VcError(RuntimeError):
@@ -110,6 +110,12 @@ class VcGptWeights(C.Structure):
                [(n, _p) for n in ("wte", "wpe", "lnf_g", "lnf_b", "lmh_w", "lmh_cs", "lmh_b")] + [("layer", C.POINTER(VcGptLayer))]
 
 
+class VcBeamState(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "nb", "max_len", "eos")] + \
+               [(n, _p) for n in ("running_scores", "running_seqs", "fin_seqs", "fin_scores", "fin_done", "fin_len", "unsatisfied",
+                                  "flags", "stopped", "src_rows", "next_tok")]
+
+
 class VcKvCache(C.Structure):
     _fields_ = [("kv", _p), ("slot", _p)] + [(n, C.c_int32) for n in ("layers", "n_seq", "heads", "s_max", "head_dim")]
 
@@ -145,6 +151,9 @@ _SIGNATURES = {
     "vc_skinny_gemm_partial": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "vc_beam_step": (_i, [_p, C.c_longlong, _i, _i, _i, _p, _i, _i, _p, _f, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "vc_beam_reorder": (_i, [_p, _p, _p, _i, _i, _i, _p]),
+    "vc_beam_init": (_i, [C.POINTER(VcBeamState), _p]),
+    "vc_beam_update": (_i, [C.POINTER(VcBeamState), _p, _p, _i, _i, _f, _p]),
+    "vc_beam_finalize": (_i, [C.POINTER(VcBeamState), _p, _p, _p]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

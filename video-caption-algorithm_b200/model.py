@@ -51,6 +51,10 @@ class _Encoder:
         self._m = owner
 
     def __call__(self, video: torch.Tensor) -> torch.Tensor:
+        with torch.cuda.device(self._m.device):       # kernels, func attributes and streams belong to the MODEL's device
+            return self._call(video)
+
+    def _call(self, video: torch.Tensor) -> torch.Tensor:
         m = self._m
         if video.dtype == torch.uint8:
             feat, _ = m.encode_prefix(video)
@@ -68,12 +72,12 @@ class _Encoder:
             return torch.zeros(B, d["video_dim"], device=m.device, dtype=torch.float32)
         patches = m.ws.patches(n)
         lib = L.load()
-        L.check(lib.vc_patchify_f32(video.data_ptr(), patches.data_ptr(), n, H, W, d["patch"], d["k_pad"], L.current_stream()))
+        L.check(lib.vc_patchify_f32(video.data_ptr(), patches.data_ptr(), n, H, W, d["patch"], d["k_pad"], L.current_stream(m.device)))
         cls = m._encode_patches(patches, n)
         feat = torch.empty(B, d["video_dim"], device=m.device, dtype=torch.float32)
-        L.check(lib.vc_vit_pool_temporal(cls.data_ptr(), 0, B, T, 1, d["vit_dim"], 0, m._pooled(B).data_ptr(), L.current_stream()))
+        L.check(lib.vc_vit_pool_temporal(cls.data_ptr(), 0, B, T, 1, d["vit_dim"], 0, m._pooled(B).data_ptr(), L.current_stream(m.device)))
         L.check(lib.vc_linear_bias_f32(m._pooled(B).data_ptr(), m.packed.vit.head_w, m.packed.vit.head_b, feat.data_ptr(), B,
-                                       d["vit_dim"], d["video_dim"], L.current_stream()))
+                                       d["vit_dim"], d["video_dim"], L.current_stream(m.device)))
         return feat
 
 
@@ -87,13 +91,17 @@ class _Mapper:
         self.last_error = ""
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        with torch.cuda.device(self._m.device):
+            return self._call(x)
+
+    def _call(self, x: torch.Tensor) -> torch.Tensor:
         m = self._m
         shape = x.shape
         x2 = x.to(device=m.device, dtype=torch.float32).reshape(-1, shape[-1]).contiguous()
         out_f = m.packed.mapper_w.shape[0]
         y = torch.empty(x2.shape[0], out_f, device=m.device, dtype=torch.float32)
         L.check(L.load().vc_linear_bias_f32(x2.data_ptr(), m.packed.mapper_w.data_ptr(), m.packed.mapper_b.data_ptr(), y.data_ptr(),
-                                            x2.shape[0], x2.shape[1], out_f, L.current_stream()))
+                                            x2.shape[0], x2.shape[1], out_f, L.current_stream(m.device)))
         return y.reshape(*shape[:-1], out_f)
 
 
@@ -108,10 +116,14 @@ class _Wte:
         self._m = owner
 
     def __call__(self, ids: torch.Tensor) -> torch.Tensor:
+        with torch.cuda.device(self._m.device):
+            return self._call(ids)
+
+    def _call(self, ids: torch.Tensor) -> torch.Tensor:
         m = self._m
         flat = ids.to(device=m.device, dtype=torch.int32).reshape(-1).contiguous()
         out = torch.empty(flat.numel(), m.dims["gpt_dim"], device=m.device, dtype=torch.float32)
-        L.check(L.load().vc_gpt2_embed_tokens(C.byref(m.packed.gpt), flat.data_ptr(), flat.numel(), out.data_ptr(), L.current_stream()))
+        L.check(L.load().vc_gpt2_embed_tokens(C.byref(m.packed.gpt), flat.data_ptr(), flat.numel(), out.data_ptr(), L.current_stream(m.device)))
         return out.reshape(*ids.shape, m.dims["gpt_dim"])
 
 
@@ -142,6 +154,10 @@ class _Gpt2:
 
     def __call__(self, inputs_embeds: torch.Tensor, attention_mask=None, past_key_values: Optional[KvCache] = None,
                  use_cache: bool = True, return_dict: bool = True, s_max: Optional[int] = None) -> _GptOutput:
+        with torch.cuda.device(self._m.device):
+            return self._call(inputs_embeds, past_key_values, s_max)
+
+    def _call(self, inputs_embeds, past_key_values, s_max) -> _GptOutput:
         m = self._m
         n_seq, Lnew, H = inputs_embeds.shape
         cache = past_key_values
@@ -151,7 +167,7 @@ class _Gpt2:
         ws = m.ws.gpt(n_seq, n_seq * Lnew)
         logits = torch.empty(n_seq, m.dims["vocab_pad"], device=m.device, dtype=torch.float32)
         L.check(L.load().vc_gpt2_forward(C.byref(m.packed.gpt), emb.data_ptr(), n_seq, Lnew, cache.length, C.byref(cache.c),
-                                         ws.data_ptr(), ws.numel(), logits.data_ptr(), 0, L.current_stream()))
+                                         ws.data_ptr(), ws.numel(), logits.data_ptr(), 0, L.current_stream(m.device)))
         cache.length += Lnew
         # HF returns [B, L, V]; only the last position is ever read on this path (benchmark_baseline.py:210)
         return _GptOutput(logits[:, : m.dims["vocab"]].unsqueeze(1), cache)
@@ -236,7 +252,7 @@ class B200CaptionModel:
         ws = self.ws.vit(chunk)
         cls = self.ws.cls(n_frames)
         L.check(L.load().vc_vit_encode(C.byref(self.packed.vit), patches.data_ptr(), n_frames, chunk, ws.data_ptr(), ws.numel(),
-                                       cls.data_ptr(), L.current_stream()))
+                                       cls.data_ptr(), L.current_stream(self.device)))
         return cls
 
     def encode_prefix(self, frames_u8: torch.Tensor):
@@ -247,6 +263,10 @@ class B200CaptionModel:
             raise ValueError(f"expect uint8 [B,T,H,W,3], got {frames_u8.dtype} {tuple(frames_u8.shape)}")
         if frames_u8.device != self.device:
             raise ValueError("frames must already live on the model's device (use caption_from_host for host buffers)")
+        with torch.cuda.device(self.device):
+            return self._encode_prefix(frames_u8)
+
+    def _encode_prefix(self, frames_u8: torch.Tensor):
         frames_u8 = frames_u8.contiguous()
         d = self.dims
         if frames_u8.numel() > 0 and tuple(frames_u8.shape[2:4]) != (self.image_size, self.image_size):
@@ -257,7 +277,7 @@ class B200CaptionModel:
         if n == 0:         # empty batch (or no frames): empty outputs, like the reference's modules on a 0-row tensor
             return (torch.zeros(B, d["video_dim"], device=self.device), torch.zeros(B, d["prefix_len"], d["gpt_dim"], device=self.device))
         lib = L.load()
-        st = L.current_stream()
+        st = L.current_stream(self.device)
         patches = self.ws.patches(n)
         torch.cuda.nvtx.range_push("Preprocessing")
         L.check(lib.vc_preprocess_u8(frames_u8.data_ptr(), self.packed.lut.data_ptr(), patches.data_ptr(), n, H, W, 1, d["patch"],
@@ -282,7 +302,8 @@ class B200CaptionModel:
         """The benchmark's greedy KV-cache loop (benchmark_baseline.py:160-240) with the bookkeeping on the
         device.  Returns (ids int32 [B,max_new] eos-padded, lengths int32 [B], logits or None)."""
         from .decoding import greedy_decode
-        return greedy_decode(self, prefix, prompt_ids or [EOS], max_new_tokens, forced_ids, keep_logits, use_graph)
+        with torch.cuda.device(self.device):
+            return greedy_decode(self, prefix, prompt_ids or [EOS], max_new_tokens, forced_ids, keep_logits, use_graph)
 
     def caption_ids(self, frames_u8: torch.Tensor, max_new_tokens: int = 20, num_beams: int = 1, prompt_ids=None, **hf_kwargs):
         """frames -> token ids.  num_beams == 1: benchmark greedy; > 1: HF beam search semantics."""

@@ -88,5 +88,5 @@ class FrameResizer:
             self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
         lib = L.load()
         L.check(lib.vc_resize_bilinear_u8(src.data_ptr(), n, H, W, self._scratch.data_ptr(), out.data_ptr(), self.out_h, self.out_w,
-                                          kx.data_ptr(), bx.data_ptr(), ksx, ky.data_ptr(), by.data_ptr(), ksy, L.current_stream()))
+                                          kx.data_ptr(), bx.data_ptr(), ksx, ky.data_ptr(), by.data_ptr(), ksy, L.current_stream(self.device)))
         return out.view(*lead, self.out_h, self.out_w, 3)
