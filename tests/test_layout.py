@@ -122,3 +122,30 @@ def test_layernorm_folding_identity():
     # and against the textbook form with unrounded weights: only the bf16 rounding of W' separates them
     full = torch.nn.functional.layer_norm(x, (H,), gamma.double(), beta.double(), 1e-5) @ w.double().t() + b.double()
     assert (folded - full).abs().max().item() < 0.05
+
+
+def test_microbatcher_worker_failure_fails_every_request():
+    """serving.MicroBatcher: if the worker thread dies (here: the pipeline cannot be built) every pending request's Future gets the
+    exception and later submits are refused — nothing hangs.  Also: pinned staging is keyed by the frame shape, not the group size."""
+    from vcb200.serving import MicroBatcher, _PinnedRing
+
+    class _Boom:
+        def pipeline(self, **kw):
+            raise RuntimeError("boom")
+
+    mb = MicroBatcher(_Boom(), max_batch=4)
+    vid = torch.zeros(2, 8, 8, 3, dtype=torch.uint8)
+    try:
+        fut = mb.submit(vid)
+        with pytest.raises(RuntimeError):
+            fut.result(timeout=30)
+    except RuntimeError:
+        pass                                   # the worker had already failed: submit itself refuses
+    mb._thread.join(timeout=30)
+    assert isinstance(mb.error, RuntimeError)
+    with pytest.raises(RuntimeError):
+        mb.submit(vid)
+    if torch.cuda.is_available():
+        ring = _PinnedRing((2, 8, 8, 3), max_batch=4, depth=3)
+        a, b = ring.next(1), ring.next(4)
+        assert a.shape == (1, 2, 8, 8, 3) and b.shape == (4, 2, 8, 8, 3) and len(ring.bufs) == 3 and a.is_pinned()

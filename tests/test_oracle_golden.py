@@ -131,3 +131,18 @@ def test_sample_warpers_equal_transformers_processors():
         assert torch.equal(torch.isinf(got), torch.isinf(want))
         assert torch.equal(got[~torch.isinf(got)], want[~torch.isinf(want)])
         assert int((~torch.isinf(got)).sum(dim=-1).max()) <= 50
+
+
+def test_postprocess_equals_reference_clean_text_and_ranker(golden_dir):
+    """a13: vcb200.postprocess (clean_text, score_sentence, select_best) gives exactly what the reference's
+    core/postprocessing functions gave on the pinned corpus (oracle/pin_text_against_reference.py)."""
+    import json
+    from vcb200 import postprocess as PP
+    g = json.loads((golden_dir / "text_cleanup.json").read_text())
+    for raw, want in g["clean"]:
+        assert PP.clean_text(raw) == want, raw
+    for s, want in g["score"]:
+        assert PP.score_sentence(s) == pytest.approx(want, abs=1e-12), s
+    for cands, want in g["select"]:
+        key, text, score = PP.select_best([tuple(c) for c in cands])
+        assert [key, text] == want[:2] and score == pytest.approx(want[2], abs=1e-12)

@@ -104,8 +104,10 @@ class InferenceEngine:
                  clean_text: Optional[Callable[[str], str]] = None, select_best: Optional[Callable] = None):
         self.config = config
         self.model = load_caption_model(config, state_dict, tokenizer)
-        self._clean = clean_text or (lambda s: s)
-        self._select = select_best
+        # core/engine.py:75-83: clean_text on every candidate, select_best over the three (host string work; postprocess.py)
+        from . import postprocess
+        self._clean = clean_text or postprocess.clean_text
+        self._select = select_best or postprocess.select_best
 
     @classmethod
     def from_config(cls, config: InferenceConfig, **kw):

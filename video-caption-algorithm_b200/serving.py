@@ -34,16 +34,34 @@ def group_requests(shapes: List[Tuple[int, ...]], max_batch: int) -> List[List[i
     return order
 
 
+class _PinnedRing:
+    """Pinned staging for the batches of ONE frame shape [T,H,W,3]: `depth` buffers of `max_batch` videos each, used in rotation
+    (a buffer is not rewritten while its H2D copy may still be running) and sliced to the size of the batch at hand."""
+
+    def __init__(self, frame_shape: Tuple[int, ...], max_batch: int, depth: int):
+        self.bufs = [torch.empty((max_batch,) + tuple(frame_shape), dtype=torch.uint8).pin_memory() for _ in range(depth)]
+        self.i = 0
+        self.bytes = sum(b.numel() for b in self.bufs)
+
+    def next(self, n: int) -> torch.Tensor:
+        b = self.bufs[self.i % len(self.bufs)]
+        self.i += 1
+        return b[:n]
+
+
 class MicroBatcher:
-    def __init__(self, model, max_batch: int = 64, max_delay_ms: float = 5.0, max_new_tokens: int = 20, decode_group: int = 2):
+    def __init__(self, model, max_batch: int = 64, max_delay_ms: float = 5.0, max_new_tokens: int = 20, decode_group: int = 2,
+                 max_pinned_bytes: int = 4 << 30):
         self.model = model
         self.max_batch, self.max_delay = int(max_batch), float(max_delay_ms) / 1e3
         self.max_new = int(max_new_tokens)
         self._q: "queue.Queue" = queue.Queue()
         self._closed = False
         self._decode_group = int(decode_group)
+        self._max_pinned = int(max_pinned_bytes)  # page-locked staging memory is bounded: least recently used frame shapes are dropped
         self.batches = 0                      # statistics: batches submitted / requests served
         self.served = 0
+        self.error: BaseException | None = None   # set if the worker died; every pending and later request fails with it
         self._thread = threading.Thread(target=self._run, name="vcb200-microbatcher", daemon=True)
         self._thread.start()
 
@@ -51,12 +69,16 @@ class MicroBatcher:
     def submit(self, frames_u8: torch.Tensor) -> Future:
         """frames_u8: uint8 [T,H,W,3] host tensor of ONE video (any frame size; resized on the GPU like the reference's
         transform).  Returns a Future whose result is (ids: list[int] without the eos padding, length)."""
+        if self.error is not None:
+            raise RuntimeError("MicroBatcher worker failed") from self.error
         if self._closed:
             raise RuntimeError("MicroBatcher is closed")
         if frames_u8.dtype != torch.uint8 or frames_u8.ndim != 4 or frames_u8.shape[-1] != 3:
             raise ValueError(f"expect uint8 [T,H,W,3], got {frames_u8.dtype} {tuple(frames_u8.shape)}")
         fut: Future = Future()
         self._q.put((frames_u8, fut))
+        if self.error is not None and not fut.done():          # the worker died between the check above and the put
+            fut.set_exception(self.error)
         return fut
 
     def close(self) -> None:
@@ -96,11 +118,42 @@ class MicroBatcher:
         return reqs, False
 
     def _run(self) -> None:
-        pipe = self.model.pipeline(max_new_tokens=self.max_new, decode_group=self._decode_group)
+        """Worker thread.  Any exception that escapes the serving loop (a failed pinned allocation, a CUDA error in the pipeline)
+        fails every queued and in-flight request and closes the batcher — a dead worker must never leave a Future hanging."""
         inflight: list = []                   # (ticket, futures)
-        staging: Dict[Tuple[int, ...], list] = {}
-        used: Dict[Tuple[int, ...], int] = {}
+        try:
+            self._serve(inflight)
+        except BaseException as e:            # noqa: BLE001
+            self.error = e
+            self._closed = True
+            for _, futs in inflight:
+                for f in futs:
+                    if not f.done():
+                        f.set_exception(e)
+            while True:
+                try:
+                    r = self._q.get_nowait()
+                except queue.Empty:
+                    break
+                if r is not None and not r[1].done():
+                    r[1].set_exception(e)
+
+    def _serve(self, inflight: list) -> None:
+        pipe = self.model.pipeline(max_new_tokens=self.max_new, decode_group=self._decode_group)
+        from collections import OrderedDict
+        rings: "OrderedDict[Tuple[int, ...], _PinnedRing]" = OrderedDict()     # keyed by the FRAME shape, least recently used first
         stop = False
+
+        def ring_for(frame_shape: Tuple[int, ...]) -> _PinnedRing:
+            r = rings.pop(frame_shape, None)
+            if r is None:
+                r = _PinnedRing(frame_shape, self.max_batch, pipe.depth + 1)
+            rings[frame_shape] = r                                              # most recently used last
+            while len(rings) > 1 and sum(x.bytes for x in rings.values()) > self._max_pinned:
+                # the oldest shape's buffers may still feed a copy in flight: finish what is in flight before dropping them
+                resolve(len(inflight))
+                rings.popitem(last=False)
+            return r
 
         def resolve(n: int) -> None:
             for _ in range(min(n, len(inflight))):
@@ -120,13 +173,7 @@ class MicroBatcher:
             reqs, stop = self._gather(block=not inflight)
             if reqs:
                 for group in group_requests([tuple(r[0].shape) for r in reqs], self.max_batch):
-                    shape = (len(group),) + tuple(reqs[group[0]][0].shape)
-                    # pinned staging buffers, rotated so that a buffer is not rewritten while its H2D copy may be running
-                    ring = staging.setdefault(shape, [])
-                    if len(ring) < pipe.depth + 1:
-                        ring.append(torch.empty(shape, dtype=torch.uint8).pin_memory())
-                    used[shape] = used.get(shape, -1) + 1
-                    buf = ring[used[shape] % len(ring)]
+                    buf = ring_for(tuple(reqs[group[0]][0].shape)).next(len(group))
                     for j, i in enumerate(group):
                         buf[j].copy_(reqs[i][0])
                     futs = [reqs[i][1] for i in group]
