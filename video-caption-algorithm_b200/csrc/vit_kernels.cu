@@ -733,25 +733,47 @@ int pool_prefix(const float* cls, int B, int T, int dim, const float* head_w, co
   return 0;
 }
 
-// =========================================================================== the two CuPy hooks as operators
-// cupy_vit_pool.py:23-104 (cls / gap, fp32 or 16-bit input, fp32 accumulate).  One warp per
-// (video, 32-channel group) for gap so the token loop is spread over lanes' channels coalesced.
+// vit_fused_pool_temporal (core/operators/cupy_vit_pool.py:127-186): feat [bsz*T, tokens, C] -> [bsz, C], the temporal mean of the
+// class token (cls) or of the mean over the patch tokens (gap).  One CTA per (video, 32-channel group): lane = channel, so every
+// row a warp touches is one 128-byte (fp32) / 64-byte (bf16) segment; the T x rows-per-frame rows are dealt round-robin to the
+// 8 warps with four loads in flight each, and the warps' partial sums are added in warp order (fixed summation order).
 template <typename T_in>
 __global__ void __launch_bounds__(256) vit_pool_kernel(const T_in* __restrict__ x, float* __restrict__ y, int bsz, int T, int tokens,
                                                        int C, int gap) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= bsz * C) return;
-  const int b = idx / C, c = idx - b * C;
+  __shared__ float s_part[8][32];
+  const int groups = (C + 31) / 32;
+  const int b = blockIdx.x / groups, c = (blockIdx.x - b * groups) * 32 + (threadIdx.x & 31);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p0 = gap ? 1 : 0, per = gap ? tokens - 1 : 1, rows = T * per;
   float acc = 0.f;
-  const int p0 = gap ? 1 : 0, p1 = gap ? tokens : 1;
-  for (int t = 0; t < T; ++t)
-    for (int p = p0; p < p1; ++p) acc += static_cast<float>(x[((static_cast<long long>(b) * T + t) * tokens + p) * C + c]);
-  y[idx] = acc / static_cast<float>(T * (p1 - p0));
+  if (c < C) {
+    for (int r0 = warp; r0 < rows; r0 += 32) {          // rows r0, r0 + 8, r0 + 16, r0 + 24 of this warp
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + 8 * u;
+        v[u] = 0.f;
+        if (r < rows) {
+          const int t = r / per, p = p0 + (r - t * per);
+          v[u] = static_cast<float>(x[((static_cast<long long>(b) * T + t) * tokens + p) * C + c]);
+        }
+      }
+      acc += (v[0] + v[1]) + (v[2] + v[3]);
+    }
+  }
+  s_part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && c < C) {
+    float s = s_part[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) s += s_part[w][lane];
+    y[static_cast<long long>(b) * C + c] = s / static_cast<float>(rows);
+  }
 }
 int vit_pool_temporal(const void* feat, int is_bf16, int bsz, int T, int tokens, int C, int gap, float* out, cudaStream_t s) {
   VC_REQUIRE(bsz >= 0 && T > 0 && tokens > (gap ? 1 : 0) && C > 0, "vit_pool: bad shape");
   if (bsz == 0) return 0;
-  const int grid = (bsz * C + 255) / 256;
+  const int grid = bsz * ((C + 31) / 32);
   if (is_bf16)
     VC_LAUNCH("vit_pool", 0.0, s, (vit_pool_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(feat), out, bsz, T, tokens, C, gap)));
   else
