@@ -412,7 +412,9 @@ def run_b200(args):
             past = None
             for k in range(n_new):
                 torch.cuda.synchronize(); w0 = _time.perf_counter()
+                torch.cuda.nvtx.range_push(f"GPT2_Decoder_Step/token_{k:02d}")         # the harness's per-token range (:193)
                 out = gpt2(inputs_embeds=x, past_key_values=past, use_cache=True, return_dict=True, s_max=a.prefix_len + 1 + n_new)
+                torch.cuda.nvtx.range_pop()
                 nxt = torch.argmax(out.logits[:, -1, :], dim=-1)
                 past = out.past_key_values
                 x = gpt2.transformer.wte(nxt).unsqueeze(1)
@@ -479,6 +481,15 @@ def run_b200(args):
             "kernels_one_encoder_pass": kern,
             "sample_ids": ids[0, :8].tolist(),
             "gather_ok": gather_ok,
+            # the same single-batch figures under the key names of the reference harness's summary (benchmark_baseline.py:352-385)
+            "harness": {"status": "ok", "batch_size": B,
+                        "ViT_Latency": {"mean_ms": round(enc_ms, 3), "note": "Preprocessing + ViT_Encoder + Cross_Modal_Alignment are one fused stage here"},
+                        "GPT2_Latency": {"mean_ms": round(dec_ms, 3)},
+                        "GPT2_token_step": {"p50_ms": round(step_p50 / 1e3, 4), "synced_p50_ms": round(step_synced_p50 / 1e3, 4)},
+                        "End_to_end_Latency": {"mean_ms": round(enc_ms + dec_ms, 3)},
+                        "Throughput": {"from_mean_latency_samples_per_s": round(B / ((enc_ms + dec_ms) / 1e3), 2),
+                                       "pipelined_samples_per_s": round(value / world, 2)},
+                        "generated_tokens": {"count": B, "mean": float(lens.float().mean().item()), "max": int(lens.max().item())}},
         }
         if not args.no_extra_configs:
             line["configs"] = extra_configs(model, dev_frames[:64], a, pk, dev)

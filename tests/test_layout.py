@@ -149,3 +149,29 @@ def test_microbatcher_worker_failure_fails_every_request():
         ring = _PinnedRing((2, 8, 8, 3), max_batch=4, depth=3)
         a, b = ring.next(1), ring.next(4)
         assert a.shape == (1, 2, 8, 8, 3) and b.shape == (4, 2, 8, 8, 3) and len(ring.bufs) == 3 and a.is_pinned()
+
+
+def test_frame_decode_pool_equals_single_thread_pil(tmp_path):
+    """frames.FrameDecodePool: JPEG files decoded by the thread pool are byte-identical to the reference's own per-file
+    `Image.open(p).convert("RGB")` (frame_loader.py:42-45), for paths and for encoded bytes, with the reference's sampling."""
+    import numpy as np
+    from PIL import Image
+    from vcb200.frames import FrameDecodePool, list_sampled_frames
+    dirs = []
+    for v in range(3):
+        d = tmp_path / f"clip{v}"
+        d.mkdir()
+        fr = synthetic.make_frames_u8(20 + v, num_frames=9, size=96).numpy()
+        for i in range(9):
+            Image.fromarray(fr[i]).save(d / f"frame_{i:06d}.jpg", quality=90)
+        dirs.append(d)
+    with FrameDecodePool(workers=4, pin=False) as pool:
+        got = pool.decode_dirs(dirs, num_frames=4).clone()
+        picks = [list_sampled_frames(d, 4) for d in dirs]
+        assert [p.name for p in picks[0]] == ["frame_000000.jpg", "frame_000002.jpg", "frame_000004.jpg", "frame_000006.jpg"]
+        want = np.stack([np.stack([np.asarray(Image.open(p).convert("RGB")) for p in ps]) for ps in picks])
+        assert got.shape == (3, 4, 96, 96, 3) and np.array_equal(got.numpy(), want)
+        as_bytes = [[p.read_bytes() for p in ps] for ps in picks]
+        assert np.array_equal(pool.decode(as_bytes).numpy(), want)
+        with pytest.raises(ValueError):
+            pool.decode([picks[0], picks[1][:3]])

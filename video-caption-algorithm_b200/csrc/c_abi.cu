@@ -366,8 +366,11 @@ static int gpt_forward_impl(const VcGptWeights* w, const float* embeds, int n_se
     if ((e = chain_add_pos_stats(w, embeds, cb, n_seq, L, past_len, s))) return e;
     return chain_layers(w, cb, n_seq, L, past_len, cache, logits_out, w->vocab_pad, s);
   }
-  // VC_PREFILL_TCGEN05=1 (A/B switch, read per call): multi-position forwards take the tcgen05 GEMM path as before
-  const bool chain_ok = L == 1 ? n_seq <= 256 || getenv("VC_PREFILL_TCGEN05") == nullptr : getenv("VC_PREFILL_TCGEN05") == nullptr;
+  // VC_PREFILL_TCGEN05=1 (A/B switch, read per call): multi-position forwards take the tcgen05 GEMM path as before;
+  // VC_GEMM_ROWS=n (A/B switch): any forward of >= n rows takes the tcgen05 GEMM path
+  static const int gemm_rows = getenv("VC_GEMM_ROWS") != nullptr ? atoi(getenv("VC_GEMM_ROWS")) : 0;
+  const bool chain_ok = (gemm_rows <= 0 || M < gemm_rows) &&
+                        (L == 1 ? n_seq <= 256 || getenv("VC_PREFILL_TCGEN05") == nullptr : getenv("VC_PREFILL_TCGEN05") == nullptr);
   if (chain_ok && M <= kDecodeMaxRows && w->vocab_pad % 64 == 0) return gpt_step_skinny(w, embeds, n_seq, L, past_len, cache, b, logits_out, s);
   if ((e = gpt_add_pos(embeds, w->wpe, b.h, n_seq, L, past_len, H, s))) return e;
   for (int l = 0; l < w->layers; ++l) {

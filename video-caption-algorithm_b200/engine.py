@@ -117,20 +117,10 @@ class InferenceEngine:
         """frame_loader.py:13-47: sample `num_frames` of the frame_*.jpg files, decode (PIL, host), and return uint8
         [1,T,H,W,3] on the device at the files' own size; `encode_prefix` then applies the Pillow-exact resize to
         image_size x image_size on the GPU (resample.py), ToTensor/Normalize and the patch layout."""
-        from PIL import Image
-        import numpy as np
-        files = sorted(Path(frames_dir).glob("frame_*.jpg"))
-        if not files:
-            raise FileNotFoundError(f"No frame_*.jpg files found under {frames_dir}")
-        picks = [files[i] for i in sample_frame_indices(len(files), self.config.num_frames)]
-        frames = []
-        for p in picks:
-            with Image.open(p) as im:
-                a = np.asarray(im.convert("RGB"))
-            if frames and a.shape != tuple(frames[0].shape):
-                raise ValueError(f"{p}: frame size {a.shape[:2]} differs from {tuple(frames[0].shape[:2])} within one clip")
-            frames.append(torch.from_numpy(a.copy()))
-        return torch.stack(frames).unsqueeze(0).to(self.model.device)
+        from .frames import FrameDecodePool
+        if getattr(self, "_decode_pool", None) is None:
+            self._decode_pool = FrameDecodePool()          # PIL decode on a pool of host threads into pinned memory (frames.py)
+        return self._decode_pool.decode_dirs([frames_dir], self.config.num_frames).to(self.model.device, non_blocking=True)
 
     @torch.no_grad()
     def infer_frames(self, frames_u8: torch.Tensor) -> dict:
