@@ -26,6 +26,10 @@
 #include <mutex>
 #include <unordered_map>
 
+#ifndef VC_LNF_REGS
+#define VC_LNF_REGS 96
+#endif
+
 namespace vc {
 
 int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* ptr, int rows, int K, int box_rows);
@@ -246,7 +250,7 @@ __device__ __forceinline__ void epilogue_block_resid(const GemmParams& p, uint8_
 
 template <int MODE>
 // 104 registers x 448 threads leave ~19K registers per SM: one CTA of the decode chain (skinny GEMM: 18.4K) fits beside this kernel
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(MODE == VC_EPI_RESID_STATS ? 128 : (MODE >= VC_EPI_LNF_BIAS ? 96 : 80))   // x 448 / 576 threads <= 64K registers
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(MODE == VC_EPI_RESID_STATS ? 128 : (MODE >= VC_EPI_LNF_BIAS ? VC_LNF_REGS : 80))   // x 448 / 576 threads <= 64K registers
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles must sit on 1024-byte boundaries (same offsets in both CTAs of the pair)

@@ -162,9 +162,12 @@ _lib = None
 
 def load(build_if_missing: bool = True) -> C.CDLL:
     """dlopen the in-tree library (RTLD_GLOBAL not needed: plain C ABI)."""
-    global _lib
+    global _lib, SO_PATH
     if _lib is not None:
         return _lib
+    if os.environ.get("VC_LIB"):                 # A/B builds of the same ABI (tools only): load this file, never rebuild it
+        SO_PATH = Path(os.environ["VC_LIB"])
+        build_if_missing = False
     if build_if_missing and needs_build():
         # on the GPU box the prebuilt .so travels with the snapshot; rebuild when stale.  A failed rebuild is an error:
         # binding today's signatures to yesterday's binary would run outdated kernels with mismatched argument lists.
