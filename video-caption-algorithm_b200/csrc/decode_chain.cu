@@ -515,10 +515,14 @@ dc_nk_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restric
 
 // ------------------------------------------------------------------------------------------------ lm_head + argmax candidates
 // logits[r][n] = rstd_r * (sum_k hb[row(r)][k] Wf[n][k] - mean_r cs[n]) + bf[n],  row(r) = (m0 + r) * row_stride + row_offset
-// (last position of every sequence).  grid = (G, row tiles of 64): a CTA streams a contiguous range of 32-feature tiles
-// (weights double-buffered in registers, K split over the 8 warps as above), keeps a running (max, lowest index) per row,
-// and writes ONE candidate per row; logits are stored only when a buffer is given (teacher-forced tests, beam search).
-template <int KB>
+// (last position of every sequence).  grid = (G, row tiles of 64).  A CTA owns a contiguous range of 16-feature tiles; every WARP
+// takes whole tiles (w, w + 8, ... of the range) and runs all 64 rows and the full K of a tile by itself, streaming the tile's
+// weights through registers in K chunks of 192 (double-buffered, the next chunk — of this or of the warp's next tile — always in
+// flight), so there is no cross-warp reduction and no __syncthreads after the activations have landed.  (The first version split K
+// over the 8 warps like dc_fullk_kernel: its shared-memory reduction per tile cost as much as the MMAs — 33 us per step.)  Each
+// lane keeps a running (max, lowest index) for the 8 rows it sees; one candidate per row and CTA leaves at the end; logits are
+// stored only when a buffer is given (teacher-forced tests, beam search).
+template <int KB>   // K = 256 * KB = 8 chunks... K / 192 or K / 256 chunks of CK k32-blocks
 __global__ void __launch_bounds__(DC_THREADS, 1)
 dc_lmhead_kernel(const __nv_bfloat16* __restrict__ hb, const float2* __restrict__ stat, int n_part, long long stat_plane, long long row_stride,
                  long long row_offset, const __nv_bfloat16* __restrict__ W, const float* __restrict__ cs, const float* __restrict__ bf, int vocab,
@@ -526,30 +530,36 @@ dc_lmhead_kernel(const __nv_bfloat16* __restrict__ hb, const float2* __restrict_
                  int* __restrict__ cand_i) {
   constexpr int K = DC_THREADS * KB;
   constexpr int PITCH = K * 2 + 64;
-  constexpr int RP = 40;                               // 32 features + 8: conflict-free float2 stores / float4 loads
+  constexpr int CK = KB == 3 ? 6 : 8;                  // k32 blocks per register chunk: 192 (K = 768) or 256 (K = 1024) columns
+  constexpr int NCH = (K / 32) / CK;                   // chunks per tile: 4
   extern __shared__ __align__(128) uint8_t dc_smem[];
   uint8_t* xs = dc_smem;                                                       // [64][PITCH]
-  float* red = reinterpret_cast<float*>(dc_smem + 64 * PITCH);                 // [8][64][RP]
-  float2* s_mr = reinterpret_cast<float2*>(red + DC_WARPS * 64 * RP);          // [64] (mean, rstd)
+  float2* s_mr = reinterpret_cast<float2*>(dc_smem + 64 * PITCH);              // [64] (mean, rstd)
   float2* s_part = s_mr + 64;                                                  // [16 parts][64 rows]
+  float* s_bv = reinterpret_cast<float*>(s_part + DC_MAX_PARTS * 64);          // [8 warps][64 rows] best value
+  int* s_bi = reinterpret_cast<int*>(s_bv + DC_WARPS * 64);                    // [8 warps][64 rows] best index
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int m0 = blockIdx.y * 64;
-  const int tiles = vocab_pad >> 5;
+  const int tiles = vocab_pad >> 4;
   const int t_begin = static_cast<int>(static_cast<long long>(tiles) * blockIdx.x / gridDim.x);
   const int t_end = static_cast<int>(static_cast<long long>(tiles) * (blockIdx.x + 1) / gridDim.x);
   Trace tr(6);
   pdl_launch_dependents();       // at entry (see dc_fullk_kernel)
 
-  uint4 wA[4][KB], wB[4][KB];
-  auto load_w = [&](uint4 (&w)[4][KB], int tile) {
+  // this warp's chunk stream: tile t_begin + warp + 8 i, chunk c of it
+  uint4 wA[2][CK], wB[2][CK];
+  auto load_w = [&](uint4 (&w)[2][CK], int tile, int ch) {
 #pragma unroll
-    for (int nf = 0; nf < 4; ++nf)
+    for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-      for (int kb = 0; kb < KB; ++kb)
-        w[nf][kb] = ldg_nc(W + static_cast<size_t>(tile * 32 + nf * 8 + g) * K + (warp * KB + kb) * 32 + 8 * t);
+      for (int kb = 0; kb < CK; ++kb)
+        w[nt][kb] = ldg_nc(W + static_cast<size_t>(tile * 16 + nt * 8 + g) * K + (ch * CK + kb) * 32 + 8 * t);
   };
-  if (t_begin < t_end) load_w(wA, t_begin);
-  if (t_begin + 1 < t_end) load_w(wB, t_begin + 1);
+  int tile = t_begin + warp;
+  if (tile < t_end) {
+    load_w(wA, tile, 0);
+    load_w(wB, tile, 1);
+  }
   pdl_wait();
   tr.mark(2);
   {
@@ -569,98 +579,103 @@ dc_lmhead_kernel(const __nv_bfloat16* __restrict__ hb, const float2* __restrict_
     }
     cp_async_commit();
   }
-  const int e_row = tid >> 2, e_q = tid & 3;           // epilogue: 64 rows x 4 lanes, 8 consecutive features each
-  float best = -INFINITY;
-  int best_i = 0x7fffffff;
   cp_async_wait<0>();
   tr.mark(3);
   __syncthreads();                                     // activations and partial statistics visible
   if (tid < 64) s_mr[tid] = row_mean_rstd_smem(s_part, n_part, 64, tid, K, eps);
   __syncthreads();
-  const float2 mr = s_mr[e_row];
-  const uint32_t xb0 = smem_u32(xs) + static_cast<uint32_t>((warp * KB * 32 + 8 * t) * 2);
+  // rows of this lane: mt * 16 + g and + 8  ->  index 2 mt, 2 mt + 1
+  float mean[8], rstd[8], best[8];
+  int best_i[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float2 mr = s_mr[(q >> 1) * 16 + g + (q & 1) * 8];
+    mean[q] = mr.x; rstd[q] = mr.y;
+    best[q] = -INFINITY; best_i[q] = 0x7fffffff;
+  }
+  const uint32_t xrow = smem_u32(xs) + g * PITCH + t * 16;
 
-  auto one_tile = [&](const uint4 (&w)[4][KB]) {
-    float acc[4][4][4];
+  float acc[4][2][4];
+  auto mma_chunk = [&](const uint4 (&w)[2][CK], int ch) {
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-      for (int nf = 0; nf < 4; ++nf) acc[mt][nf][0] = acc[mt][nf][1] = acc[mt][nf][2] = acc[mt][nf][3] = 0.f;
-#pragma unroll
-    for (int kb = 0; kb < KB; ++kb) {
+    for (int kb = 0; kb < CK; ++kb) {
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt) {
-        const uint4 xa = lds128(xb0 + (mt * 16 + g) * PITCH + kb * 64), xb = lds128(xb0 + (mt * 16 + g + 8) * PITCH + kb * 64);
-#pragma unroll
-        for (int nf = 0; nf < 4; ++nf) mma16816(acc[mt][nf], xa.x, xb.x, xa.y, xb.y, w[nf][kb].x, w[nf][kb].y);
-#pragma unroll
-        for (int nf = 0; nf < 4; ++nf) mma16816(acc[mt][nf], xa.z, xb.z, xa.w, xb.w, w[nf][kb].z, w[nf][kb].w);
+        const uint4 xa = lds128(xrow + mt * 16 * PITCH + (ch * CK + kb) * 64), xb = lds128(xrow + (mt * 16 + 8) * PITCH + (ch * CK + kb) * 64);
+        mma16816(acc[mt][0], xa.x, xb.x, xa.y, xb.y, w[0][kb].x, w[0][kb].y);
+        mma16816(acc[mt][1], xa.x, xb.x, xa.y, xb.y, w[1][kb].x, w[1][kb].y);
+        mma16816(acc[mt][0], xa.z, xb.z, xa.w, xb.w, w[0][kb].z, w[0][kb].w);
+        mma16816(acc[mt][1], xa.z, xb.z, xa.w, xb.w, w[1][kb].z, w[1][kb].w);
       }
     }
-    float* rw = red + warp * 64 * RP;
+  };
+  for (; tile < t_end; tile += DC_WARPS) {
+    const int f0 = tile * 16;
+    // epilogue constants of this tile (columns nt * 8 + 2 t, + 1): requested before the MMAs
+    float2 c_s[2], c_b[2];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      c_s[nt] = __ldg(reinterpret_cast<const float2*>(cs + f0 + nt * 8 + 2 * t));
+      c_b[nt] = __ldg(reinterpret_cast<const float2*>(bf + f0 + nt * 8 + 2 * t));
+    }
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-      for (int nf = 0; nf < 4; ++nf) {
-        *reinterpret_cast<float2*>(rw + (mt * 16 + g) * RP + nf * 8 + 2 * t) = make_float2(acc[mt][nf][0], acc[mt][nf][1]);
-        *reinterpret_cast<float2*>(rw + (mt * 16 + g + 8) * RP + nf * 8 + 2 * t) = make_float2(acc[mt][nf][2], acc[mt][nf][3]);
+      for (int nt = 0; nt < 2; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+    const int next = tile + DC_WARPS;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ch += 2) {
+      mma_chunk(wA, ch);
+      if (ch + 2 < NCH) load_w(wA, tile, ch + 2);
+      else if (next < t_end) load_w(wA, next, 0);
+      mma_chunk(wB, ch + 1);
+      if (ch + 3 < NCH) load_w(wB, tile, ch + 3);
+      else if (next < t_end) load_w(wB, next, 1);
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int col = f0 + nt * 8 + 2 * t;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {               // rows mt * 16 + g (h2 = 0) and + 8 (h2 = 1)
+          const int q = 2 * mt + h2;
+          const float y0 = rstd[q] * (acc[mt][nt][2 * h2] - mean[q] * c_s[nt].x) + c_b[nt].x;
+          const float y1 = rstd[q] * (acc[mt][nt][2 * h2 + 1] - mean[q] * c_s[nt].y) + c_b[nt].y;
+          if (col < vocab && y0 > best[q]) { best[q] = y0; best_i[q] = col; }            // increasing index, strict '>'
+          if (col + 1 < vocab && y1 > best[q]) { best[q] = y1; best_i[q] = col + 1; }
+          const int r = m0 + mt * 16 + g + 8 * h2;
+          if (logits != nullptr && r < n_rows) *reinterpret_cast<float2*>(logits + static_cast<size_t>(r) * ld + col) = make_float2(y0, y1);
+        }
       }
-  };
-  auto finish_tile = [&](int tile, const float4& c_lo, const float4& c_hi, const float4& b_lo, const float4& b_hi) {
-    const float* rr = red + e_row * RP + e_q * 8;
-    float4 s0 = *reinterpret_cast<const float4*>(rr), s1 = *reinterpret_cast<const float4*>(rr + 4);
+  }
+  // lanes t = 0..3 of a row group hold different columns of the same rows; then the 8 warps; ties -> lowest index
 #pragma unroll
-    for (int ww = 1; ww < DC_WARPS; ++ww) {              // fixed order
-      const float4 a = *reinterpret_cast<const float4*>(rr + ww * 64 * RP), b = *reinterpret_cast<const float4*>(rr + ww * 64 * RP + 4);
-      s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
-      s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
-    }
-    float y[8];
-    y[0] = mr.y * (s0.x - mr.x * c_lo.x) + b_lo.x; y[1] = mr.y * (s0.y - mr.x * c_lo.y) + b_lo.y;
-    y[2] = mr.y * (s0.z - mr.x * c_lo.z) + b_lo.z; y[3] = mr.y * (s0.w - mr.x * c_lo.w) + b_lo.w;
-    y[4] = mr.y * (s1.x - mr.x * c_hi.x) + b_hi.x; y[5] = mr.y * (s1.y - mr.x * c_hi.y) + b_hi.y;
-    y[6] = mr.y * (s1.z - mr.x * c_hi.z) + b_hi.z; y[7] = mr.y * (s1.w - mr.x * c_hi.w) + b_hi.w;
-    const int f0 = tile * 32 + e_q * 8;
+  for (int q = 0; q < 8; ++q) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (f0 + i < vocab && y[i] > best) { best = y[i]; best_i = f0 + i; }     // increasing index, strict '>': lowest index of a tie
-    if (logits != nullptr && m0 + e_row < n_rows) {
-      float* o = logits + static_cast<size_t>(m0 + e_row) * ld + f0;
-      *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
-      *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
+    for (int o = 1; o <= 2; o <<= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best[q], o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i[q], o);
+      if (ov > best[q] || (ov == best[q] && oi < best_i[q])) { best[q] = ov; best_i[q] = oi; }
     }
-  };
-  for (int tile = t_begin; tile < t_end; tile += 2) {
-    {
-      const float4 c_lo = __ldg(reinterpret_cast<const float4*>(cs + tile * 32 + e_q * 8)), c_hi = __ldg(reinterpret_cast<const float4*>(cs + tile * 32 + e_q * 8 + 4));
-      const float4 b_lo = __ldg(reinterpret_cast<const float4*>(bf + tile * 32 + e_q * 8)), b_hi = __ldg(reinterpret_cast<const float4*>(bf + tile * 32 + e_q * 8 + 4));
-      one_tile(wA);
-      if (tile + 2 < t_end) load_w(wA, tile + 2);
-      __syncthreads();
-      finish_tile(tile, c_lo, c_hi, b_lo, b_hi);
-      __syncthreads();
-    }
-    if (tile + 1 < t_end) {
-      const int tl = tile + 1;
-      const float4 c_lo = __ldg(reinterpret_cast<const float4*>(cs + tl * 32 + e_q * 8)), c_hi = __ldg(reinterpret_cast<const float4*>(cs + tl * 32 + e_q * 8 + 4));
-      const float4 b_lo = __ldg(reinterpret_cast<const float4*>(bf + tl * 32 + e_q * 8)), b_hi = __ldg(reinterpret_cast<const float4*>(bf + tl * 32 + e_q * 8 + 4));
-      one_tile(wB);
-      if (tl + 2 < t_end) load_w(wB, tl + 2);
-      __syncthreads();
-      finish_tile(tl, c_lo, c_hi, b_lo, b_hi);
-      __syncthreads();
+    if (t == 0) {
+      const int row = (q >> 1) * 16 + g + (q & 1) * 8;
+      s_bv[warp * 64 + row] = best[q];
+      s_bi[warp * 64 + row] = best_i[q];
     }
   }
-  // the 4 lanes of a row (adjacent lanes) -> one candidate; ties -> lowest index
+  __syncthreads();
+  if (tid < 64 && m0 + tid < n_rows) {
+    float bv = s_bv[tid];
+    int bi = s_bi[tid];
 #pragma unroll
-  for (int o = 1; o <= 2; o <<= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-    if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
-  }
-  if (e_q == 0 && m0 + e_row < n_rows) {
-    cand_v[static_cast<size_t>(m0 + e_row) * gridDim.x + blockIdx.x] = best;
-    cand_i[static_cast<size_t>(m0 + e_row) * gridDim.x + blockIdx.x] = best_i;
+    for (int w2 = 1; w2 < DC_WARPS; ++w2) {
+      const float ov = s_bv[w2 * 64 + tid];
+      const int oi = s_bi[w2 * 64 + tid];
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    cand_v[static_cast<size_t>(m0 + tid) * gridDim.x + blockIdx.x] = bv;
+    cand_i[static_cast<size_t>(m0 + tid) * gridDim.x + blockIdx.x] = bi;
   }
   tr.flush();
 }
@@ -826,7 +841,7 @@ int chain_set_trace(void* buf, int max_records) {
 
 bool chain_supported(const VcGptWeights* w, int rows) {
   if (w == nullptr || w->layer == nullptr || w->lmh_w == nullptr || w->lmh_cs == nullptr || w->lmh_b == nullptr) return false;
-  if (!(w->dim == 768 || w->dim == 1024) || w->heads * 64 != w->dim || w->vocab_pad % 32 != 0) return false;
+  if (!(w->dim == 768 || w->dim == 1024) || w->heads * 64 != w->dim || w->vocab_pad % 16 != 0) return false;
   if (rows <= 0 || rows > (getenv("VC_DECODE_CHAIN") != nullptr && atoi(getenv("VC_DECODE_CHAIN")) == 2 ? DC_MAX_ROWS : DC_BEST_ROWS)) return false;
   for (int l = 0; l < w->layers; ++l)
     if (w->layer[l].attn_wf == nullptr || w->layer[l].fc_wf == nullptr) return false;
@@ -896,13 +911,13 @@ int chain_layers(const VcGptWeights* w, const ChainBuffers& b, int n_seq, int L,
   const dim3 grid(G, (n_seq + 63) / 64);
   const auto* lw = static_cast<const __nv_bfloat16*>(w->lmh_w);
   if (H == 768) {
-    constexpr size_t smem = 64 * (768 * 2 + 64) + DC_WARPS * 64 * 40 * 4 + 64 * 8 + DC_MAX_PARTS * 64 * 8;
+    constexpr size_t smem = 64 * (768 * 2 + 64) + 64 * 8 + DC_MAX_PARTS * 64 * 8 + 2 * DC_WARPS * 64 * 4;
     if ((e = set_smem(dc_lmhead_kernel<3>, smem))) return e;
     VC_LAUNCH("dc_lm_head", static_cast<double>(w->vocab_pad) * H * 2.0, s,
               VC_CUDA_OK(launch_pdl(dc_lmhead_kernel<3>, grid, dim3(DC_THREADS), smem, s, hb, stat, parts, static_cast<long long>(M), static_cast<long long>(L),
                                     static_cast<long long>(L - 1), lw, w->lmh_cs, w->lmh_b, w->vocab, w->vocab_pad, n_seq, eps, logits, ld, b.cand_v, b.cand_i)));
   } else {
-    constexpr size_t smem = 64 * (1024 * 2 + 64) + DC_WARPS * 64 * 40 * 4 + 64 * 8 + DC_MAX_PARTS * 64 * 8;
+    constexpr size_t smem = 64 * (1024 * 2 + 64) + 64 * 8 + DC_MAX_PARTS * 64 * 8 + 2 * DC_WARPS * 64 * 4;
     if ((e = set_smem(dc_lmhead_kernel<4>, smem))) return e;
     VC_LAUNCH("dc_lm_head", static_cast<double>(w->vocab_pad) * H * 2.0, s,
               VC_CUDA_OK(launch_pdl(dc_lmhead_kernel<4>, grid, dim3(DC_THREADS), smem, s, hb, stat, parts, static_cast<long long>(M), static_cast<long long>(L),
