@@ -115,6 +115,26 @@ def test_eos_branch_finishes_at_chosen_steps_under_teacher_forcing():
     _decisive_ids_equal(ids.cpu(), ids_o, lens_o, t2[..., 0] - t2[..., 1], stop_at_tie=False)
 
 
+def test_many_row_chain_is_repeatable():
+    """The tensor-core chain (>= 128 rows) ends every residual GEMM with a "last CTA combines the row statistics" step: the
+    same 256 prefixes must give the same ids and logits on every run, with and without other work on the GPU."""
+    a, sd, m = _model("vit_b16_gpt2", chunk_frames=1024)
+    g = torch.Generator().manual_seed(11)
+    prefixes = (torch.randn(256, a.prefix_len, a.gpt_dim, generator=g) * 0.5).to(DEV)
+    ids0, lens0, lg0 = m.greedy_ids(prefixes, None, 20, keep_logits=True)
+    ids0, lg0 = ids0.clone(), lg0.clone()
+    side = torch.cuda.Stream()
+    big = torch.randn(4096, 4096, device=DEV)
+    for it in range(12):
+        if it % 2:
+            with torch.cuda.stream(side):
+                for _ in range(4):
+                    big @ big
+        ids, lens, lg = m.greedy_ids(prefixes, None, 20, keep_logits=True)
+        torch.cuda.synchronize()
+        assert torch.equal(ids, ids0) and torch.equal(lg, lg0), f"run {it} differs"
+
+
 # ------------------------------------------------------------------------------------------------------------------ cfg2
 def test_cfg2_pipeline_at_bench_size_against_oracle():
     """BASELINE.json configs[1]: 64 videos x 16 frames, full depth, greedy 20 tokens — the exact path bench.py times

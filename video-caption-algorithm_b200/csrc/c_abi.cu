@@ -77,14 +77,14 @@ static VitBuffers carve_vit(const VcVitWeights* w, int chunk_frames, void* base)
   b.delta2 = p + off;                       off += align_up(M * w->dim * 2, 1024);
   b.x_cls = reinterpret_cast<float*>(p + off); off += align_up(static_cast<size_t>(chunk_frames) * w->dim * 4, 1024);
   b.stats = reinterpret_cast<float*>(p + off); off += align_up(M * 8, 1024);                                     // (mean, rstd) per row
-  b.pstats = reinterpret_cast<float*>(p + off); off += align_up(M * 8 * 4 * ((w->dim + 255) / 256), 1024);      // partial (sum, sum sq)
+  b.pstats = reinterpret_cast<float*>(p + off); off += align_up(M * 8 * gemm_resid_parts(w->dim), 1024);      // partial (sum, sum sq)
   b.total = off;
   return b;
 }
 
 struct GptBuffers {
   float* h; void* xn; void* qkv; void* att; void* hid; float* emb; float* logits; int32_t* finished; int32_t* next; float* partial;
-  float* stat; float* cand_v; int* cand_i;
+  float* stat; float* cand_v; int* cand_i; float* pstats; unsigned int* done;
   size_t total;
 };
 constexpr int kDecodeMaxRows = 1024;  // n_seq * new positions handled by the weight-streaming kernels; beyond: tcgen05 GEMM path
@@ -112,10 +112,13 @@ static GptBuffers carve_gpt(const VcGptWeights* w, int n_seq, int max_rows, void
     m = std::max(m, static_cast<size_t>(skinny_ksplit(4 * H, H)) * 4 * H);
     m = std::max(m, static_cast<size_t>(skinny_ksplit(H, 4 * H)) * H);
     b.partial = reinterpret_cast<float*>(p + off);  off += align_up(m * rows * 4, 1024);
-    b.stat = reinterpret_cast<float*>(p + off);     off += align_up(static_cast<size_t>(16) * rows * 8, 1024);
+    b.stat = reinterpret_cast<float*>(p + off);     off += align_up(static_cast<size_t>(16) * R * 8, 1024);
     const size_t nc = static_cast<size_t>(n_seq) * 256;
     b.cand_v = reinterpret_cast<float*>(p + off);   off += align_up(nc * 4, 1024);
     b.cand_i = reinterpret_cast<int*>(p + off);     off += align_up(nc * 4, 1024);
+    // partial row statistics of the tcgen05 chain's residual epilogues (all rows: that chain also serves > 1024-row prefills)
+    b.pstats = reinterpret_cast<float*>(p + off);   off += align_up(static_cast<size_t>(gemm_resid_parts(H)) * R * 8, 1024);
+    b.done = reinterpret_cast<unsigned int*>(p + off); off += 1024;
   }
   b.total = off;
   return b;
@@ -238,19 +241,19 @@ int vc_vit_encode(const VcVitWeights* w, const void* patches_bf16, int n_frames,
       // fc2 epilogues (x += bf16(acc + bias)); both emit bf16(x_new) — the A operand of the next product, whose weights
       // carry the LayerNorm affine (packing.fold_layernorm) — and partial row statistics; (mean, rstd) are applied in the
       // consumer's epilogue.  Only the first block's input needs a pass of its own (rows come from two producers).
-      const int parts = 3 * ((D + 255) / 256);     // 3 epilogue warps per TMEM lane quarter and 256-column tile (gemm_tcgen05.cu)
+      const int parts = gemm_resid_parts(D);       // one partial-statistics slot per row and 32-column chunk
       const int gelu_f = w->gelu_tanh ? VC_EPI_LNF_GELU_TANH : VC_EPI_LNF_GELU_ERF;
       if ((e = rowstats_cast(b.x, b.xn, b.stats, M, D, 1e-6f, s))) return e;
       for (int l = 0; l < w->layers; ++l) {
         const VcVitLayer& L = w->layer[l];
-        GemmExtra ex{L.qkv_cs, b.stats, nullptr, nullptr, nullptr};
+        GemmExtra ex{L.qkv_cs, b.stats, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
         if ((e = gemm_bf16_ex(b.xn, L.qkv_wf, L.qkv_bf, M, 3 * D, D, VC_EPI_LNF_BIAS, b.qkv, 3 * D, nullptr, 0, 0, &ex, s))) return e;
         if (l + 1 == w->layers) break;
         if ((e = vit_attention(b.qkv, b.att, nf, N, w->heads, 64, s))) return e;
-        GemmExtra ep{nullptr, nullptr, b.x, b.xn, b.pstats};
+        GemmExtra ep{nullptr, nullptr, b.x, b.xn, b.pstats, nullptr, nullptr, 0.f};
         if ((e = gemm_bf16_ex(b.att, L.proj_w, L.proj_b, M, D, D, VC_EPI_RESID_STATS, nullptr, D, nullptr, 0, 0, &ep, s))) return e;
         if ((e = ln_stats_finalize(b.pstats, parts, M, D, 1e-6f, b.stats, s))) return e;
-        GemmExtra e1{L.fc1_cs, b.stats, nullptr, nullptr, nullptr};
+        GemmExtra e1{L.fc1_cs, b.stats, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
         if ((e = gemm_bf16_ex(b.xn, L.fc1_wf, L.fc1_bf, M, w->mlp, D, gelu_f, b.hid, w->mlp, nullptr, 0, 0, &e1, s))) return e;
         if ((e = gemm_bf16_ex(b.hid, L.fc2_w, L.fc2_b, M, D, w->mlp, VC_EPI_RESID_STATS, nullptr, D, nullptr, 0, 0, &ep, s))) return e;
         if ((e = ln_stats_finalize(b.pstats, parts, M, D, 1e-6f, b.stats, s))) return e;
@@ -357,6 +360,41 @@ static int gpt_step_skinny(const VcGptWeights* w, const float* embeds, int n_seq
   return skinny_gemm(b.xn, w->wte, logits_out, n_seq, w->vocab_pad, H, 1, s);
 }
 
+// Forwards of many rows (the prefill of a caption batch, grouped decode steps, beam steps: 128-1280+ rows) on the tcgen05 GEMM with
+// 64-column tiles: QKV (LayerNorm folded) -> attention -> proj (residual + statistics in the epilogue) -> finalize -> fc1 (folded,
+// gelu_new) -> fc2 (residual + statistics) -> finalize: the encoder's scheme on GPT-2's folded weights; every
+// launch is a programmatic dependent launch.  lm_head: ln_f on the last rows + tied lm_head GEMM (fp32 logits).
+static bool use_gemm_chain(const VcGptWeights* w, int rows) {
+  static const int min_rows = getenv("VC_GEMM_ROWS") != nullptr ? atoi(getenv("VC_GEMM_ROWS")) : 128;
+  if (min_rows <= 0 || rows < min_rows) return false;
+  if (w->dim % 64 != 0 || w->vocab_pad % 32 != 0) return false;
+  for (int l = 0; l < w->layers; ++l)
+    if (w->layer[l].attn_wf == nullptr || w->layer[l].fc_wf == nullptr) return false;
+  return true;
+}
+static int gpt_forward_gemm_chain(const VcGptWeights* w, const float* embeds, int n_seq, int L, int past_len, VcKvCache* cache,
+                                  const GptBuffers& b, float* logits_out, cudaStream_t s) {
+  const int H = w->dim, M = n_seq * L;
+  int e;
+  VC_CUDA_OK(cudaMemsetAsync(b.done, 0, sizeof(unsigned int), s));     // the residual epilogues' "CTAs done" counter
+  if ((e = gpt_add_pos(embeds, w->wpe, b.h, n_seq, L, past_len, H, s))) return e;
+  if ((e = rowstats_cast(b.h, b.xn, b.stat, M, H, 1e-5f, s))) return e;
+  for (int l = 0; l < w->layers; ++l) {
+    const VcGptLayer& Ly = w->layer[l];
+    GemmExtra eq{Ly.attn_cs, b.stat, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
+    if ((e = gemm_bf16_ex(b.xn, Ly.attn_wf, Ly.attn_bf, M, 3 * H, H, VC_EPI_LNF_BIAS, b.qkv, 3 * H, nullptr, 0, 0, &eq, s))) return e;
+    if ((e = gpt_attention(b.qkv, nullptr, 0, nullptr, b.att, cache, l, n_seq, L, past_len, s))) return e;
+    // residual update + statistics; the last CTA to finish also turns the partials into (mean, rstd): no finalize kernel
+    GemmExtra er{nullptr, nullptr, b.h, b.xn, b.pstats, b.stat, b.done, 1e-5f};
+    if ((e = gemm_bf16_ex(b.att, Ly.aproj_w, Ly.aproj_b, M, H, H, VC_EPI_RESID_STATS, nullptr, H, nullptr, 0, 0, &er, s))) return e;
+    GemmExtra ef{Ly.fc_cs, b.stat, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
+    if ((e = gemm_bf16_ex(b.xn, Ly.fc_wf, Ly.fc_bf, M, 4 * H, H, VC_EPI_LNF_GELU_TANH, b.hid, 4 * H, nullptr, 0, 0, &ef, s))) return e;
+    if ((e = gemm_bf16_ex(b.hid, Ly.mproj_w, Ly.mproj_b, M, H, 4 * H, VC_EPI_RESID_STATS, nullptr, H, nullptr, 0, 0, &er, s))) return e;
+  }
+  if ((e = layernorm_rows(b.h, L, L - 1, w->lnf_g, w->lnf_b, nullptr, b.xn, n_seq, H, 1e-5f, s))) return e;
+  return gemm_bf16(b.xn, w->wte, nullptr, n_seq, w->vocab_pad, H, VC_EPI_BIAS_F32, logits_out, w->vocab_pad, nullptr, 0, 0, s);
+}
+
 static int gpt_forward_impl(const VcGptWeights* w, const float* embeds, int n_seq, int L, int past_len, VcKvCache* cache,
                             const GptBuffers& b, float* logits_out, cudaStream_t s) {
   const int H = w->dim, M = n_seq * L;
@@ -366,11 +404,10 @@ static int gpt_forward_impl(const VcGptWeights* w, const float* embeds, int n_se
     if ((e = chain_add_pos_stats(w, embeds, cb, n_seq, L, past_len, s))) return e;
     return chain_layers(w, cb, n_seq, L, past_len, cache, logits_out, w->vocab_pad, s);
   }
-  // VC_PREFILL_TCGEN05=1 (A/B switch, read per call): multi-position forwards take the tcgen05 GEMM path as before;
-  // VC_GEMM_ROWS=n (A/B switch): any forward of >= n rows takes the tcgen05 GEMM path
-  static const int gemm_rows = getenv("VC_GEMM_ROWS") != nullptr ? atoi(getenv("VC_GEMM_ROWS")) : 0;
-  const bool chain_ok = (gemm_rows <= 0 || M < gemm_rows) &&
-                        (L == 1 ? n_seq <= 256 || getenv("VC_PREFILL_TCGEN05") == nullptr : getenv("VC_PREFILL_TCGEN05") == nullptr);
+  // forwards of >= 128 rows (VC_GEMM_ROWS=n moves the threshold, 0 switches it off): the tcgen05 chain above
+  if (use_gemm_chain(w, M)) return gpt_forward_gemm_chain(w, embeds, n_seq, L, past_len, cache, b, logits_out, s);
+  // VC_PREFILL_TCGEN05=1 (A/B switch, read per call): multi-position forwards take the plain tcgen05 GEMM path as in round 1
+  const bool chain_ok = L == 1 ? n_seq <= 256 || getenv("VC_PREFILL_TCGEN05") == nullptr : getenv("VC_PREFILL_TCGEN05") == nullptr;
   if (chain_ok && M <= kDecodeMaxRows && w->vocab_pad % 64 == 0) return gpt_step_skinny(w, embeds, n_seq, L, past_len, cache, b, logits_out, s);
   if ((e = gpt_add_pos(embeds, w->wpe, b.h, n_seq, L, past_len, H, s))) return e;
   for (int l = 0; l < w->layers; ++l) {

@@ -37,16 +37,20 @@ int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* ptr, int rows, int K, int
 namespace {
 
 constexpr int BM = 128;                // rows of A per CTA; a pair covers 256
-constexpr int BN = 256;                // columns per pair tile; each CTA stages BN/2 rows of W
 constexpr int BK = 64, UK = 16;
-// 4 stages measure the same as 6 on every ViT shape (the ring only has to cover the L2 latency), and 161 KB instead of
-// 225 KB of shared memory leaves room on each SM for the small decode-step kernels of the PREVIOUS batch to run
-// underneath the encoder GEMMs of the next one (model.py: CaptionPipeline).
-constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;          // 16 KB
-constexpr int B_BYTES = (BN / 2) * BK * 2;    // 16 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int TMEM_COLS = 512;         // 2 accumulators x 256 fp32 columns
+// Two tile widths (BN = columns per pair tile; each CTA stages BN/2 rows of W):
+//   256: the encoder's shapes (thousands of tiles).  4 ring stages measure the same as 6 on every ViT shape (the ring only has to
+//        cover the L2 latency).
+//    64: few-row products (GPT-2 prefill / grouped decode steps of 128-1280 rows: ONE row tile): N/64 pairs instead of N/256
+//        stream the weights, and a deeper ring (7 x 20 KB) because each pair walks its whole K with nothing else to overlap.
+template <int BN>
+struct Tile {
+  static constexpr int STAGES = BN == 256 ? 4 : 7;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = BN == 256 ? 512 : 128;      // 2 accumulators x BN fp32 columns (power of two >= 32)
+};
 // Epilogue warps per CTA: a multiple of 4 (a warp reads the TMEM lane quarter warp % 4).  The bf16-output epilogues are
 // instruction-bound (ncu: the GELU epilogue executes 3x the instructions of the bias one and holds the tensor pipe at 68 %
 // active), so they get 16 warps = two 32-column chunks each; the residual + statistics epilogue waits on HBM, keeps a block
@@ -55,7 +59,10 @@ __host__ __device__ constexpr int epi_warps(int mode) { return mode == VC_EPI_RE
 constexpr int EPI_WARPS_MAX = 16;
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // one 32x32 fp32 block per warp
 __host__ __device__ constexpr int gemm_threads(int mode) { return (2 + epi_warps(mode)) * 32; }
-__host__ __device__ constexpr int gemm_smem(int mode) { return STAGES * STAGE_BYTES + epi_warps(mode) * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/; }
+__host__ __device__ constexpr int gemm_smem(int mode, int bn) {
+  return (bn == 256 ? Tile<256>::STAGES * Tile<256>::STAGE_BYTES : Tile<64>::STAGES * Tile<64>::STAGE_BYTES) + epi_warps(mode) * EPI_STAGE_BYTES +
+         1024 /*align*/ + 256 /*barriers*/;
+}
 
 struct GemmParams {
   int M, N, K;
@@ -70,7 +77,10 @@ struct GemmParams {
   const float2* stats;    // [M] (mean, rstd) of the rows of A's source
   float* xres;            // fp32 residual stream [M, N], read-modify-written (RESID_STATS)
   __nv_bfloat16* xb_out;  // bf16 [M, N]: bf16 copy of the new residual = A operand of the next folded product
-  float2* pstats;         // [parts][M] partial (sum, sum of squares) of the new residual rows, parts = 3 * ceil(N/256)
+  float2* pstats;         // [N/32][M] partial (sum, sum of squares) of the new residual rows, one slot per 32-column chunk
+  float2* stats_out;      // RESID_STATS, few rows: the LAST CTA to finish turns the partials into (mean, rstd) per row here
+  unsigned int* done;     // ... counter of finished CTAs (zero before the launch; the last CTA resets it)
+  float eps;
 };
 
 // Predicated global accesses as single instructions: a C++ `if` around the store lets the compiler sink the whole
@@ -216,8 +226,7 @@ __device__ __forceinline__ void epilogue_park(uint8_t* stg, int lane, const uint
   }
   __syncwarp();
 }
-__device__ __forceinline__ void epilogue_block_resid(const GemmParams& p, uint8_t* stg, int lane, int row_base, int col0, const float4 (&xv)[8],
-                                                     float (&ssum)[8], float (&ssq)[8]) {
+__device__ __forceinline__ void epilogue_block_resid(const GemmParams& p, uint8_t* stg, int lane, int row_base, int col0, const float4 (&xv)[8]) {
   const uint32_t sbase = smem_u32(stg);
   const int cc = lane & 7, rsub = lane >> 3;
   const int col = col0 + cc * 4;
@@ -242,21 +251,26 @@ __device__ __forceinline__ void epilogue_block_resid(const GemmParams& p, uint8_
       s1 += __shfl_xor_sync(0xffffffffu, s1, o2);
       s2 += __shfl_xor_sync(0xffffffffu, s2, o2);
     }
-    ssum[i] += s1;
-    ssq[i] += s2;
+    // one slot per (32-column chunk, row): the grouping does not depend on the tile width or on which warp ran the chunk, so the
+    // statistics — and with them every later bit — are the same whatever batch a row rides in
+    if (cc == 0 && ok) p.pstats[static_cast<size_t>(col0 >> 5) * p.M + row] = make_float2(s1, s2);
   }
   __syncwarp();   // the next block reuses the staging buffer
 }
 
-template <int MODE>
-// 104 registers x 448 threads leave ~19K registers per SM: one CTA of the decode chain (skinny GEMM: 18.4K) fits beside this kernel
+template <int MODE, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(MODE == VC_EPI_RESID_STATS ? 128 : (MODE >= VC_EPI_LNF_BIAS ? VC_LNF_REGS : 80))   // x 448 / 576 threads <= 64K registers
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles must sit on 1024-byte boundaries (same offsets in both CTAs of the pair)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  constexpr int STAGES = Tile<BN>::STAGES, B_BYTES = Tile<BN>::B_BYTES, STAGE_BYTES = Tile<BN>::STAGE_BYTES, TMEM_COLS = Tile<BN>::TMEM_COLS;
+  (void)B_BYTES;
   uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;
   constexpr int EPI_WARPS = epi_warps(MODE);
+  // Dependents may become resident early (their barrier init / TMEM allocation then overlaps this kernel's tail); this kernel itself
+  // touches no global memory before pdl_wait() below.  No-ops when the kernel is not part of a programmatic-dependent-launch chain.
+  pdl_launch_dependents();
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EPI_WARPS * EPI_STAGE_BYTES);   // used in the leader only
   uint64_t* empty_bar = full_bar + STAGES;    // per CTA: its smem slot is free (multicast commit)
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2] per CTA: accumulator ready (multicast commit)
@@ -284,6 +298,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   cluster_sync_all();          // barriers initialised and TMEM allocated in both CTAs before any cross-CTA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                  // the predecessor's outputs (A, residual stream, statistics) are complete and visible from here on
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (whole warp loops, one elected lane issues)
@@ -343,7 +358,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const int ew = warp - 2;            // 0..7
     const int quarter = warp & 3;       // TMEM lane quarter this warp may read
     const int part = ew >> 2;           // which column chunks of the 256-wide tile: 0 -> 0..2, 1 -> 3..5, 2 -> 6..7
-    const int c_begin = EPI_WARPS == 16 ? part * 2 : part * 3, c_end = EPI_WARPS == 16 ? part * 2 + 2 : (part == 2 ? 8 : part * 3 + 3);
+    // 32-column chunks of the tile dealt to the warp groups: 8 chunks / 4 groups = 2 each, / 3 groups = (0-2, 3-5, 6-7); a 64-wide
+    // tile has 2 chunks, so some groups get none (they still take part in the accumulator hand-off)
+    constexpr int CHUNKS = BN / 32, GROUPS = EPI_WARPS / 4;
+    const int c_begin = (part * CHUNKS + GROUPS - 1) / GROUPS, c_end = ((part + 1) * CHUNKS + GROUPS - 1) / GROUPS;
     uint8_t* stg = epi_stage + ew * EPI_STAGE_BYTES;
     const uint32_t tempty_leader0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     const uint32_t tempty_leader1 = mapa_shared(smem_u32(&tempty_bar[1]), 0);
@@ -358,9 +376,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       tc_fence_after();
       const int row_base = m0 + quarter * 32;
       if (MODE == VC_EPI_RESID_STATS) {
-        float ssum[8], ssq[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) ssum[i] = ssq[i] = 0.f;
 #pragma unroll 1
         for (int c = c_begin; c < c_end; ++c) {
           uint32_t r[32];
@@ -379,27 +394,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             const int t2 = t + n_pairs;
             resid_prefetch(p, lane, (t2 / n_tiles) * (2 * BM) + static_cast<int>(rank) * BM + quarter * 32, (t2 % n_tiles) * BN + c_begin * 32, xnext);
           }
-          if (live) epilogue_block_resid(p, stg, lane, row_base, col0, xcur, ssum, ssq);
+          if (live) epilogue_block_resid(p, stg, lane, row_base, col0, xcur);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
-        // partial statistics of this warp's column chunks of this tile: slot (n tile, part) of the row
-        if ((lane & 7) == 0 && n0 + c_begin * 32 < p.N) {
-          float2* ps = p.pstats + static_cast<size_t>((t % n_tiles) * (EPI_WARPS / 4) + part) * p.M;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = row_base + i * 4 + (lane >> 3);
-            if (row < p.M) ps[row] = make_float2(ssum[i], ssq[i]);
-          }
-        }
       } else {
         float2 st[8];
         if (MODE >= VC_EPI_LNF_BIAS) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int row = row_base + i * 4 + (lane >> 3);
-            st[i] = __ldg(p.stats + (row < p.M ? row : 0));
+            st[i] = __ldcg(p.stats + (row < p.M ? row : 0));     // written by the kernel before this one: not the read-only path
           }
         }
 #pragma unroll 1
@@ -419,6 +425,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (MODE == VC_EPI_RESID_STATS && p.stats_out != nullptr) {
+      // Few rows (GPT-2 chains): no separate finalize kernel.  Every CTA counts itself done once its epilogue warps have stored
+      // their partials; the last one combines the N/32 partials of every row (same arithmetic as ln_stats_finalize_kernel).
+      __shared__ unsigned int s_last;
+      __threadfence();                                                            // this thread's partials are out before the count
+      asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");          // the epilogue warps of this CTA
+      if (threadIdx.x == 64) {
+        __threadfence();
+        s_last = atomicAdd(p.done, 1u) == gridDim.x - 1 ? 1u : 0u;
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+      if (s_last) {
+        __threadfence();
+        const int parts = p.N >> 5;
+        for (int row = static_cast<int>(threadIdx.x) - 64; row < p.M; row += EPI_WARPS * 32) {
+          double sm = 0.0, sq = 0.0;
+          for (int c = 0; c < parts; ++c) {
+            const float2 v = __ldcg(p.pstats + static_cast<size_t>(c) * p.M + row);
+            sm += v.x; sq += v.y;
+          }
+          const double mean = sm / p.N;
+          double var = sq / p.N - mean * mean;
+          var = var > 0.0 ? var : 0.0;
+          p.stats_out[row] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps))));
+        }
+        if (threadIdx.x == 64) *p.done = 0u;
+      }
     }
   }
 
@@ -449,27 +483,32 @@ int make_map(CUtensorMap* tm, const void* ptr, int rows, int K, int box_rows) { 
 
 int g_num_sms = 0;
 std::mutex g_cfg_mu;
-PerDeviceOnce g_attr_set[16];
+PerDeviceOnce g_attr_set[16][2];
 
-template <int MODE>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t stream) {
+template <int MODE, int BN>
+int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t stream) {
   {
     std::lock_guard<std::mutex> lk(g_cfg_mu);
-    if (g_attr_set[MODE].first()) {
-      VC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(MODE)));
-      // ask for the largest shared-memory carve-out, not the smallest that holds SMEM_BYTES: what is left over (~45 KB)
-      // is where the decode chain's CTAs of the previous batch run beside this kernel's resident CTAs (CaptionPipeline)
-      VC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (g_attr_set[MODE][BN == 256 ? 0 : 1].first()) {
+      VC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(MODE, BN)));
+      VC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE, BN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
   }
   static const char* const kNames[] = {"gemm_bias", "gemm_gelu_erf", "gemm_gelu_tanh", "gemm_resid", "gemm_f32", "gemm_patch",
                                        "gemm_lnf_bias", "gemm_lnf_gelu_erf", "gemm_lnf_gelu_tanh", "gemm_resid_stats"};
   {
     KernelScope ks(kNames[MODE], 2.0 * p.M * static_cast<double>(p.N) * p.K, stream);
-    gemm_tcgen05_kernel<MODE><<<grid, gemm_threads(MODE), gemm_smem(MODE), stream>>>(ta, tb, p);
+    // programmatic dependent launch: inside the GPT-2 chains the next kernel's prologue overlaps this kernel's tail; after a
+    // kernel that never triggers (the encoder's plain launches) it behaves like an ordinary launch
+    VC_CUDA_OK(launch_pdl(gemm_tcgen05_kernel<MODE, BN>, dim3(grid), dim3(gemm_threads(MODE)), static_cast<size_t>(gemm_smem(MODE, BN)), stream, ta, tb, p));
   }
   VC_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+template <int MODE>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, int bn, cudaStream_t stream) {
+  return bn == 256 ? launch_bn<MODE, 256>(ta, tb, p, grid, stream) : launch_bn<MODE, 64>(ta, tb, p, grid, stream);
 }
 
 }  // namespace
@@ -491,6 +530,29 @@ int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* ptr, int rows, int K, int
   return 0;
 }
 
+static int current_sms() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  static int sms_of[64] = {0};
+  if (dev >= 0 && dev < 64 && sms_of[dev] != 0) return sms_of[dev];
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  if (dev >= 0 && dev < 64) sms_of[dev] = n;
+  return n;
+}
+
+// Tile width the GEMM uses for an [M, N] output: 256 columns when that already gives every CTA pair a tile, else 64
+// (few-row products).  VC_GEMM_BN=64|256 forces one (A/B).
+int gemm_tile_width(int M, int N) {
+  static const int force_bn = getenv("VC_GEMM_BN") ? atoi(getenv("VC_GEMM_BN")) : 0;
+  if (force_bn == 64 || force_bn == 256) return force_bn;
+  const int m_tiles = (M + 2 * BM - 1) / (2 * BM);
+  const int sms = current_sms();
+  return m_tiles * ((N + 255) / 256) >= (sms > 0 ? sms : 148) / 2 ? 256 : 64;
+}
+// partial (sum, sum of squares) slots per row the RESID_STATS epilogue writes: one per 32-column chunk (ln_stats_finalize's `parts`)
+int gemm_resid_parts(int N) { return N / 32; }
+
 int gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int K, int mode, void* out, int ldo,
               const float* aux, int rows_per_group, int max_ctas, cudaStream_t stream) {
   return gemm_bf16_ex(A, W, bias, M, N, K, mode, out, ldo, aux, rows_per_group, max_ctas, nullptr, stream);
@@ -506,29 +568,22 @@ int gemm_bf16_ex(const void* A, const void* W, const float* bias, int M, int N, 
                  (reinterpret_cast<uintptr_t>(out) & 15) == 0,
              "gemm: operands must be 16-byte aligned");
   VC_REQUIRE(get_encode() == 0, "gemm: cuTensorMapEncodeTiled entry point not found (no CUDA driver?)");
-  {
-    int dev = 0;
-    VC_CUDA_OK(cudaGetDevice(&dev));
-    static int sms_of[64] = {0};
-    if (dev < 0 || dev >= 64 || sms_of[dev] == 0) {
-      int n = 0;
-      VC_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-      if (dev >= 0 && dev < 64) sms_of[dev] = n;
-      g_num_sms = n;
-    } else {
-      g_num_sms = sms_of[dev];
-    }
-  }
+  g_num_sms = current_sms();
+  VC_REQUIRE(g_num_sms > 0, "gemm: cannot query the device");
+  // tile width: 256 columns when that already gives every CTA pair a tile, else 64 (few-row products: one row tile)
+  const int m_tiles = (M + 2 * BM - 1) / (2 * BM);
+  const int BN = gemm_tile_width(M, N);
   CUtensorMap ta, tb;
   if (int e = make_map(&ta, A, M, K, BM)) return e;
   if (int e = make_map(&tb, W, N, K, BN / 2)) return e;
-  GemmParams p{M, N, K, mode, bias, out, ldo, aux, rows_per_group, nullptr, nullptr, nullptr, nullptr, nullptr};
+  GemmParams p{M, N, K, mode, bias, out, ldo, aux, rows_per_group, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
   if (ex != nullptr) {
     p.cs = ex->cs; p.stats = reinterpret_cast<const float2*>(ex->stats); p.xres = ex->xres;
     p.xb_out = static_cast<__nv_bfloat16*>(ex->xb_out);
     p.pstats = reinterpret_cast<float2*>(ex->pstats);
+    p.stats_out = reinterpret_cast<float2*>(ex->stats_out); p.done = ex->done; p.eps = ex->eps;
   }
-  const int total = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);   // pair tiles
+  const int total = m_tiles * ((N + BN - 1) / BN);   // pair tiles
   // VC_ENCODER_SMS=n leaves SMs free for kernels of another stream (the decode chain of the previous batch)
   static const int sm_cap = getenv("VC_ENCODER_SMS") ? atoi(getenv("VC_ENCODER_SMS")) : 0;
   int pairs = (sm_cap > 0 && sm_cap < g_num_sms ? sm_cap : g_num_sms) / 2;
@@ -536,18 +591,18 @@ int gemm_bf16_ex(const void* A, const void* W, const float* bias, int M, int N, 
   if (max_ctas > 0 && 2 * pairs > max_ctas) pairs = max_ctas / 2 > 0 ? max_ctas / 2 : 1;
   const int grid = 2 * pairs;
   switch (mode) {
-    case VC_EPI_BIAS: return launch<VC_EPI_BIAS>(ta, tb, p, grid, stream);
-    case VC_EPI_BIAS_GELU_ERF: return launch<VC_EPI_BIAS_GELU_ERF>(ta, tb, p, grid, stream);
-    case VC_EPI_BIAS_GELU_TANH: return launch<VC_EPI_BIAS_GELU_TANH>(ta, tb, p, grid, stream);
-    case VC_EPI_BIAS_RESID_F32: return launch<VC_EPI_BIAS_RESID_F32>(ta, tb, p, grid, stream);
-    case VC_EPI_BIAS_F32: return launch<VC_EPI_BIAS_F32>(ta, tb, p, grid, stream);
+    case VC_EPI_BIAS: return launch<VC_EPI_BIAS>(ta, tb, p, grid, BN, stream);
+    case VC_EPI_BIAS_GELU_ERF: return launch<VC_EPI_BIAS_GELU_ERF>(ta, tb, p, grid, BN, stream);
+    case VC_EPI_BIAS_GELU_TANH: return launch<VC_EPI_BIAS_GELU_TANH>(ta, tb, p, grid, BN, stream);
+    case VC_EPI_BIAS_RESID_F32: return launch<VC_EPI_BIAS_RESID_F32>(ta, tb, p, grid, BN, stream);
+    case VC_EPI_BIAS_F32: return launch<VC_EPI_BIAS_F32>(ta, tb, p, grid, BN, stream);
     case VC_EPI_PATCH_EMBED:
       VC_REQUIRE(aux != nullptr && rows_per_group > 0, "gemm: patch-embed epilogue needs pos embedding and patches/frame");
-      return launch<VC_EPI_PATCH_EMBED>(ta, tb, p, grid, stream);
-    case VC_EPI_LNF_BIAS: return launch<VC_EPI_LNF_BIAS>(ta, tb, p, grid, stream);
-    case VC_EPI_LNF_GELU_ERF: return launch<VC_EPI_LNF_GELU_ERF>(ta, tb, p, grid, stream);
-    case VC_EPI_LNF_GELU_TANH: return launch<VC_EPI_LNF_GELU_TANH>(ta, tb, p, grid, stream);
-    case VC_EPI_RESID_STATS: return launch<VC_EPI_RESID_STATS>(ta, tb, p, grid, stream);
+      return launch<VC_EPI_PATCH_EMBED>(ta, tb, p, grid, BN, stream);
+    case VC_EPI_LNF_BIAS: return launch<VC_EPI_LNF_BIAS>(ta, tb, p, grid, BN, stream);
+    case VC_EPI_LNF_GELU_ERF: return launch<VC_EPI_LNF_GELU_ERF>(ta, tb, p, grid, BN, stream);
+    case VC_EPI_LNF_GELU_TANH: return launch<VC_EPI_LNF_GELU_TANH>(ta, tb, p, grid, BN, stream);
+    case VC_EPI_RESID_STATS: return launch<VC_EPI_RESID_STATS>(ta, tb, p, grid, BN, stream);
     default: set_error("gemm: unknown epilogue mode %d", mode); return -1;
   }
 }

@@ -58,10 +58,17 @@ struct GemmExtra {
   const float* stats;    // LNF: float2 (mean, rstd) per row of A [M]
   float* xres;           // RESID_STATS: fp32 residual stream [M, N], x += bf16(acc + bias)
   void* xb_out;          // RESID_STATS: bf16 copy of the new residual [M, N]
-  float* pstats;         // RESID_STATS: float2 partial (sum, sum of squares) [3 * ceil(N/256)][M]
+  float* pstats;         // RESID_STATS: float2 partial (sum, sum of squares) [N/32][M], one slot per 32-column chunk
+  float* stats_out;      // RESID_STATS, optional (few rows): float2 (mean, rstd) [M] written by the last CTA to finish ...
+  unsigned int* done;    // ... which needs a device counter that is zero before the launch (it is reset to zero at the end)
+  float eps;
 };
 int gemm_bf16_ex(const void* A, const void* W, const float* bias, int M, int N, int K, int mode, void* out, int ldo,
                  const float* aux, int rows_per_group, int max_ctas, const GemmExtra* ex, cudaStream_t stream);
+// tile width (256 / 64 columns) the GEMM picks for an [M, N] output; partial-statistics slots per row its RESID_STATS epilogue
+// writes (= ln_stats_finalize's `parts`)
+int gemm_tile_width(int M, int N);
+int gemm_resid_parts(int N);
 // float2 (mean, rstd) per row from `parts` partial (sum, sum of squares) pairs over N columns in total
 int ln_stats_finalize(const float* pstats, int parts, int M, int N, float eps, float* stats, cudaStream_t s);
 // xb = bf16(x), stats = (mean, rstd) per row of the fp32 rows x [M, dim]

@@ -356,7 +356,7 @@ class CaptionPipeline:
         ids, lens = pipe.result(t0)    # host int32 tensors (pinned); blocks until that batch is done
     """
 
-    MAX_DECODE_ROWS = 256          # c_abi.cu kDecodeMaxRows: the weight-streaming decode step handles this many sequences
+    MAX_DECODE_ROWS = 256          # sequences decoded as one chain at most (a latency bound: every video of the group waits for the chain)
 
     def __init__(self, model: B200CaptionModel, max_new_tokens: int, decode_group: int = 2, overlap_decode: bool = True):
         """decode_group: consecutive batches whose sequences are decoded together (group * batch <= 256).  The decode
@@ -393,7 +393,10 @@ class CaptionPipeline:
                 copied = self.copy_stream.record_event()
             dev_frames = slot["frames"]
         else:
-            copied, dev_frames = None, frames_u8
+            # frames already on the device: the encoder stream reads them after whatever the caller's stream has queued, and the
+            # caching allocator must not hand the block to somebody else while the encoder may still be reading it
+            copied, dev_frames = torch.cuda.current_stream(m.device).record_event(), frames_u8
+            frames_u8.record_stream(self.enc_stream)
         with torch.cuda.stream(self.enc_stream):
             if copied is not None:
                 self.enc_stream.wait_event(copied)
@@ -403,8 +406,9 @@ class CaptionPipeline:
         slot["prefix"], slot["cb"], slot["to_host"], slot["done"] = prefix, after_decode, to_host, None
         self._pending.append(ticket)
         self._n += 1
-        if self._pending and (len(self._pending) >= self.group or
-                              sum(self._slots[t % self.depth]["prefix"].shape[0] for t in self._pending) * 2 > self.MAX_DECODE_ROWS):
+        # decode once the group is complete, or when another batch of this size would not fit into one decode chain
+        rows = sum(self._slots[t % self.depth]["prefix"].shape[0] for t in self._pending)
+        if len(self._pending) >= self.group or rows + prefix.shape[0] > self.MAX_DECODE_ROWS:
             self._flush()
         return ticket
 
