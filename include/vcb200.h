@@ -133,6 +133,13 @@ int vc_patchify_f32(const float* video_chw, void* out_bf16, int n_frames, int H,
 /* ---- a2  ViT encoder building blocks + whole encoder: src/models/video_encoder.py:288-326 */
 int vc_gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int K, int epilogue, void* out, int ldo,
                  const float* aux, int rows_per_group, vc_stream_t stream);
+/* The residual half of a transformer block as ONE product (video_encoder.py:168-171 `x = x + attn(...)` / `x + mlp(...)`,
+ * transformers GPT2Block residual adds):  x[M,N] (fp32, in place) += bf16(A W^T + bias);  xb = bf16(x);  and the rows' partial
+ * (sum, sum of squares) per 32-column chunk in pstats (float2 [N/32][M]) for the LayerNorm folded into the NEXT product.
+ * stats_out / done (both or neither): with few rows the last CTA turns the partials into float2 (mean, rstd) [M]; `done` is a
+ * device counter that is zero before the call.  split_k: 0 = chosen from the shape; 1, 2, 4 = forced (64-column tiles only). */
+int vc_gemm_resid_stats(const void* A, const void* W, const float* bias, int M, int N, int K, float* x, void* xb_bf16,
+                        float* pstats, float* stats_out, unsigned int* done, float eps, int split_k, vc_stream_t stream);
 int vc_layernorm_f32_bf16(const float* x, const float* gamma, const float* beta, void* out_bf16, int rows, int dim,
                           float eps, vc_stream_t stream);
 int vc_vit_attention(const void* qkv_bf16, void* out_bf16, int n_frames, int tokens, int heads, int head_dim,

@@ -121,6 +121,46 @@ def test_gemm_residual_and_f32_epilogues(lib):
     assert (out32 - _gemm_ref(A, W, None)).abs().max().item() < 2e-3
 
 
+@pytest.mark.parametrize("M,K", [(64, 768), (256, 768), (256, 3072), (320, 3072), (130, 768)])
+def test_gemm_resid_stats_split_k(lib, M, K):
+    """x += bf16(A W^T + b), xb = bf16(x), row statistics — with K walked by one CTA pair per tile and split over 2 / 4 pairs of a
+    cluster (the few-row products of the GPT-2 chain): every variant against torch, the split ones against the unsplit one to
+    accumulation-order noise, and the fused "last CTA" (mean, rstd) against torch's LayerNorm statistics."""
+    N = 768
+    torch.manual_seed(M + K)
+    A = (torch.randn(M, K, device=DEV) * 0.5).to(torch.bfloat16)
+    W = (torch.randn(N, K, device=DEV) * 0.03).to(torch.bfloat16)
+    bias = torch.randn(N, device=DEV) * 0.1
+    x0 = torch.randn(M, N, device=DEV)
+    delta = (A.float() @ W.float().t() + bias).to(torch.bfloat16).float()
+    ref = x0 + delta
+    outs = {}
+    for ks in (1, 2, 4, 0):
+        x = x0.clone()
+        xb = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+        pst = torch.full((N // 32, M, 2), float("nan"), device=DEV)
+        st = torch.zeros(M, 2, device=DEV)
+        done = torch.zeros(1, device=DEV, dtype=torch.int32)
+        L.check(lib.vc_gemm_resid_stats(A.data_ptr(), W.data_ptr(), bias.data_ptr(), M, N, K, x.data_ptr(), xb.data_ptr(), pst.data_ptr(),
+                                        st.data_ptr(), done.data_ptr(), 1e-5, ks, _stream()))
+        torch.cuda.synchronize()
+        assert int(done.item()) == 0                              # the last CTA resets the counter
+        # one bf16 ulp of the delta (|delta| <~ 4 -> 2^-6) where the accumulation order moved a rounding boundary
+        assert (x - ref).abs().max().item() <= 0.04, ks
+        assert torch.equal(xb, x.to(torch.bfloat16)), ks
+        chunks = x.view(M, N // 32, 32)
+        assert torch.allclose(pst[..., 0].t(), chunks.sum(-1), atol=2e-4, rtol=1e-5), ks
+        assert torch.allclose(pst[..., 1].t(), (chunks * chunks).sum(-1), atol=2e-3, rtol=1e-5), ks
+        mean = x.double().mean(-1)
+        rstd = 1.0 / torch.sqrt(x.double().var(-1, unbiased=False) + 1e-5)
+        assert torch.allclose(st[:, 0].double(), mean, atol=1e-5, rtol=1e-5), ks
+        assert torch.allclose(st[:, 1].double(), rstd, atol=1e-5, rtol=1e-5), ks
+        outs[ks] = x
+    for ks in (2, 4):
+        d = (outs[ks] - outs[1]).abs()
+        assert d.max().item() <= 0.04 and (d > 0).float().mean().item() < 0.02, ks     # same values up to rare rounding flips
+
+
 def test_gemm_patch_embed_epilogue(lib):
     frames, P, D, K = 3, 196, 768, 768
     M = frames * P

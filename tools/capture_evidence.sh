@@ -1,3 +1,6 @@
+# Evidence run for profiles/: launch lists and --set full captures of the encoder GEMMs, the 256-row decode chain and the beam
+# step, each ncu command only after the same command has exited 0 without ncu.  Run on the GPU box: bash tools/capture_evidence.sh
+# (writes gpurun_out/r2c_*; summarise here with tools/launch_summary.py and tools/ncu_summary.py).
 set -x
 K='gemm_tcgen05|layernorm|vit_|preprocess|pool_prefix|rowstats|ln_stats|cls_rows'
 python tools/prof_encoder.py 2 > gpurun_out/r2c_plain_enc.log 2>&1 || exit 1

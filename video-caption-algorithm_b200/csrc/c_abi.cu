@@ -137,7 +137,7 @@ using namespace vc;
 extern "C" {
 
 const char* vc_last_error(void) { return g_err; }
-int vc_abi_version(void) { return 4; }
+int vc_abi_version(void) { return 5; }
 int vc_num_sms(void) {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
@@ -200,6 +200,15 @@ int vc_gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, 
   return gemm_bf16(A, W, bias, M, N, K, epilogue, out, ldo, aux, rows_per_group, 0, S(stream));
 }
 
+int vc_gemm_resid_stats(const void* A, const void* W, const float* bias, int M, int N, int K, float* x, void* xb_bf16, float* pstats,
+                        float* stats_out, unsigned int* done, float eps, int split_k, vc_stream_t stream) {
+  VC_REQUIRE(x != nullptr && xb_bf16 != nullptr && pstats != nullptr && bias != nullptr, "gemm_resid_stats: null operand");
+  VC_REQUIRE((stats_out == nullptr) == (done == nullptr), "gemm_resid_stats: stats_out and done go together");
+  VC_REQUIRE(split_k == 0 || split_k == 1 || split_k == 2 || split_k == 4, "gemm_resid_stats: split_k=%d", split_k);
+  GemmExtra ex{nullptr, nullptr, x, xb_bf16, pstats, stats_out, done, eps, split_k};
+  return gemm_bf16_ex(A, W, bias, M, N, K, VC_EPI_RESID_STATS, xb_bf16, N, nullptr, 0, 0, &ex, S(stream));
+}
+
 int vc_layernorm_f32_bf16(const float* x, const float* gamma, const float* beta, void* out_bf16, int rows, int dim, float eps,
                           vc_stream_t stream) {
   return layernorm_f32_bf16(x, gamma, beta, out_bf16, rows, dim, eps, S(stream));
@@ -246,14 +255,14 @@ int vc_vit_encode(const VcVitWeights* w, const void* patches_bf16, int n_frames,
       if ((e = rowstats_cast(b.x, b.xn, b.stats, M, D, 1e-6f, s))) return e;
       for (int l = 0; l < w->layers; ++l) {
         const VcVitLayer& L = w->layer[l];
-        GemmExtra ex{L.qkv_cs, b.stats, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
+        GemmExtra ex{L.qkv_cs, b.stats, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0};
         if ((e = gemm_bf16_ex(b.xn, L.qkv_wf, L.qkv_bf, M, 3 * D, D, VC_EPI_LNF_BIAS, b.qkv, 3 * D, nullptr, 0, 0, &ex, s))) return e;
         if (l + 1 == w->layers) break;
         if ((e = vit_attention(b.qkv, b.att, nf, N, w->heads, 64, s))) return e;
-        GemmExtra ep{nullptr, nullptr, b.x, b.xn, b.pstats, nullptr, nullptr, 0.f};
+        GemmExtra ep{nullptr, nullptr, b.x, b.xn, b.pstats, nullptr, nullptr, 0.f, 0};
         if ((e = gemm_bf16_ex(b.att, L.proj_w, L.proj_b, M, D, D, VC_EPI_RESID_STATS, nullptr, D, nullptr, 0, 0, &ep, s))) return e;
         if ((e = ln_stats_finalize(b.pstats, parts, M, D, 1e-6f, b.stats, s))) return e;
-        GemmExtra e1{L.fc1_cs, b.stats, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
+        GemmExtra e1{L.fc1_cs, b.stats, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0};
         if ((e = gemm_bf16_ex(b.xn, L.fc1_wf, L.fc1_bf, M, w->mlp, D, gelu_f, b.hid, w->mlp, nullptr, 0, 0, &e1, s))) return e;
         if ((e = gemm_bf16_ex(b.hid, L.fc2_w, L.fc2_b, M, D, w->mlp, VC_EPI_RESID_STATS, nullptr, D, nullptr, 0, 0, &ep, s))) return e;
         if ((e = ln_stats_finalize(b.pstats, parts, M, D, 1e-6f, b.stats, s))) return e;
@@ -379,15 +388,17 @@ static int gpt_forward_gemm_chain(const VcGptWeights* w, const float* embeds, in
   VC_CUDA_OK(cudaMemsetAsync(b.done, 0, sizeof(unsigned int), s));     // the residual epilogues' "CTAs done" counter
   if ((e = gpt_add_pos(embeds, w->wpe, b.h, n_seq, L, past_len, H, s))) return e;
   if ((e = rowstats_cast(b.h, b.xn, b.stat, M, H, 1e-5f, s))) return e;
+  // residual update + statistics; the last CTA to finish also turns the partials into (mean, rstd): no finalize kernel.
+  // (Tried: the CONSUMER's epilogue warps combining the partials while its MMAs run — the producer loses its 3.5 us tail, the
+  // consumer gains 4.3 us of scattered 8-byte loads in all 16 epilogue warps: 582 us per step either way.)
+  GemmExtra er{nullptr, nullptr, b.h, b.xn, b.pstats, b.stat, b.done, 1e-5f, 0};
   for (int l = 0; l < w->layers; ++l) {
     const VcGptLayer& Ly = w->layer[l];
-    GemmExtra eq{Ly.attn_cs, b.stat, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
+    GemmExtra eq{Ly.attn_cs, b.stat, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0};
     if ((e = gemm_bf16_ex(b.xn, Ly.attn_wf, Ly.attn_bf, M, 3 * H, H, VC_EPI_LNF_BIAS, b.qkv, 3 * H, nullptr, 0, 0, &eq, s))) return e;
     if ((e = gpt_attention(b.qkv, nullptr, 0, nullptr, b.att, cache, l, n_seq, L, past_len, s))) return e;
-    // residual update + statistics; the last CTA to finish also turns the partials into (mean, rstd): no finalize kernel
-    GemmExtra er{nullptr, nullptr, b.h, b.xn, b.pstats, b.stat, b.done, 1e-5f};
     if ((e = gemm_bf16_ex(b.att, Ly.aproj_w, Ly.aproj_b, M, H, H, VC_EPI_RESID_STATS, nullptr, H, nullptr, 0, 0, &er, s))) return e;
-    GemmExtra ef{Ly.fc_cs, b.stat, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
+    GemmExtra ef{Ly.fc_cs, b.stat, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0};
     if ((e = gemm_bf16_ex(b.xn, Ly.fc_wf, Ly.fc_bf, M, 4 * H, H, VC_EPI_LNF_GELU_TANH, b.hid, 4 * H, nullptr, 0, 0, &ef, s))) return e;
     if ((e = gemm_bf16_ex(b.hid, Ly.mproj_w, Ly.mproj_b, M, H, 4 * H, VC_EPI_RESID_STATS, nullptr, H, nullptr, 0, 0, &er, s))) return e;
   }

@@ -59,9 +59,14 @@ __host__ __device__ constexpr int epi_warps(int mode) { return mode == VC_EPI_RE
 constexpr int EPI_WARPS_MAX = 16;
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // one 32x32 fp32 block per warp
 __host__ __device__ constexpr int gemm_threads(int mode) { return (2 + epi_warps(mode)) * 32; }
-__host__ __device__ constexpr int gemm_smem(int mode, int bn) {
-  return (bn == 256 ? Tile<256>::STAGES * Tile<256>::STAGE_BYTES : Tile<64>::STAGES * Tile<64>::STAGE_BYTES) + epi_warps(mode) * EPI_STAGE_BYTES +
-         1024 /*align*/ + 256 /*barriers*/;
+// Split-K (KS CTA pairs of one cluster share a 64-column tile, each walks K/KS): a 4-stage ring is enough for K/KS, and every CTA
+// owns 128/KS rows of its row half for the final epilogue: it receives the KS partial accumulators of those rows in RED_BYTES.
+constexpr int KS_STAGES = 4;
+constexpr int RED_PITCH = 64 + 4;                       // floats per row of a received partial (272 B: conflict-free float4 rows)
+constexpr int RED_BYTES = 128 * RED_PITCH * 4;          // KS sources x 128/KS rows
+__host__ __device__ constexpr int gemm_smem(int mode, int bn, int ks = 1) {
+  return (bn == 256 ? Tile<256>::STAGES * Tile<256>::STAGE_BYTES : (ks > 1 ? KS_STAGES : Tile<64>::STAGES) * Tile<64>::STAGE_BYTES) +
+         epi_warps(mode) * EPI_STAGE_BYTES + (ks > 1 ? RED_BYTES : 0) + 1024 /*align*/ + 256 /*barriers*/;
 }
 
 struct GemmParams {
@@ -75,6 +80,8 @@ struct GemmParams {
   // LayerNorm-folded and residual/statistics epilogues (GemmExtra, vc_kernels.h)
   const float* cs;        // [N] column sums of the folded weights
   const float2* stats;    // [M] (mean, rstd) of the rows of A's source
+  const void* w_ptr;      // W (for the L2 prefetch of this CTA's weight rows ahead of the dependency wait; 64-column tiles)
+  int pre_flags;          // bit 0: weight tiles of the first ring stages before the dependency wait; bit 1: L2 prefetch of the rest
   float* xres;            // fp32 residual stream [M, N], read-modify-written (RESID_STATS)
   __nv_bfloat16* xb_out;  // bf16 [M, N]: bf16 copy of the new residual = A operand of the next folded product
   float2* pstats;         // [N/32][M] partial (sum, sum of squares) of the new residual rows, one slot per 32-column chunk
@@ -258,13 +265,20 @@ __device__ __forceinline__ void epilogue_block_resid(const GemmParams& p, uint8_
   __syncwarp();   // the next block reuses the staging buffer
 }
 
-template <int MODE, int BN>
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(MODE == VC_EPI_RESID_STATS ? 128 : (MODE >= VC_EPI_LNF_BIAS ? VC_LNF_REGS : 80))   // x 448 / 576 threads <= 64K registers
+// KS > 1 (RESID_STATS with 64-column tiles only): split-K inside a cluster of KS CTA pairs.  A few-row product with N = 768 has
+// only 12 column tiles; 12 pairs each streaming all of A (256 rows x K) are bound by the L2 -> SM fill of those 24 SMs
+// (15-21 us per product at 256 rows).  With KS pairs per tile every pair walks K/KS, leaves its 128 x 64 partial accumulator in
+// TMEM, and the epilogue warps SEND each 32 x 32 block to the CTA that owns those rows (`st.shared::cluster`, one mbarrier arrive
+// per lane); the owner adds the KS partials in a fixed order and runs the ordinary residual + statistics epilogue on its
+// 128/KS rows.  One tile per cluster (grid = tiles x 2 KS CTAs).
+template <int MODE, int BN, int KS = 1>
+__global__ void __cluster_dims__(2 * KS, 1, 1) __maxnreg__(MODE == VC_EPI_RESID_STATS ? 128 : (MODE >= VC_EPI_LNF_BIAS ? VC_LNF_REGS : 80))   // x 448 / 576 threads <= 64K registers
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmParams p) {
+  static_assert(KS == 1 || (MODE == VC_EPI_RESID_STATS && BN == 64 && (KS == 2 || KS == 4)), "split-K: residual epilogue, 64-column tiles");
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles must sit on 1024-byte boundaries (same offsets in both CTAs of the pair)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  constexpr int STAGES = Tile<BN>::STAGES, B_BYTES = Tile<BN>::B_BYTES, STAGE_BYTES = Tile<BN>::STAGE_BYTES, TMEM_COLS = Tile<BN>::TMEM_COLS;
+  constexpr int STAGES = KS > 1 ? KS_STAGES : Tile<BN>::STAGES, B_BYTES = Tile<BN>::B_BYTES, STAGE_BYTES = Tile<BN>::STAGE_BYTES, TMEM_COLS = Tile<BN>::TMEM_COLS;
   (void)B_BYTES;
   uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;
   constexpr int EPI_WARPS = epi_warps(MODE);
@@ -275,21 +289,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   uint64_t* empty_bar = full_bar + STAGES;    // per CTA: its smem slot is free (multicast commit)
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2] per CTA: accumulator ready (multicast commit)
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] leader only: accumulator drained by both CTAs' epilogues
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* red_bar = tempty_bar + 2;         // split-K: the partials of this CTA's rows have arrived (256 lane arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(red_bar + 1);
+  float* red_buf = reinterpret_cast<float*>(epi_stage + EPI_WARPS * EPI_STAGE_BYTES + 256);   // split-K only (gemm_smem)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t crank = cluster_ctarank();   // KS == 1: 0 / 1
+  const uint32_t rank = crank & 1;            // row half of the pair tile
+  const uint32_t lead_rank = crank & ~1u;     // the pair's leader inside the cluster
+  const int kq = static_cast<int>(crank >> 1);   // which K share (split-K), 0 otherwise
   const bool leader = rank == 0;
-  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const uint16_t pair_mask = static_cast<uint16_t>(0x3u << lead_rank);
+  // work items: a pair tile per CTA pair, or (split-K) per cluster
+  const int pair = blockIdx.x / (2 * KS), n_pairs = gridDim.x / (2 * KS);
   const int m_tiles = (p.M + 2 * BM - 1) / (2 * BM);
   const int n_tiles = (p.N + BN - 1) / BN;
-  const int k_blocks = p.K / BK;
-  const int total = m_tiles * n_tiles;
+  const int k_blocks = p.K / BK / KS;         // K blocks this pair walks ...
+  const int kb_first = kq * k_blocks;         // ... starting here
+  const int total = KS > 1 ? min(m_tiles * n_tiles, n_pairs) : m_tiles * n_tiles;   // split-K: one tile per cluster (host: grid = tiles)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 2 * EPI_WARPS); }
+    mbar_init(red_bar, 256);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b); }
@@ -298,29 +321,55 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   cluster_sync_all();          // barriers initialised and TMEM allocated in both CTAs before any cross-CTA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();                  // the predecessor's outputs (A, residual stream, statistics) are complete and visible from here on
-
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (whole warp loops, one elected lane issues)
     int stage = 0; uint32_t phase = 0;
-    const uint32_t full_leader0 = mapa_shared(smem_u32(&full_bar[0]), 0);
+    const uint32_t full_leader0 = mapa_shared(smem_u32(&full_bar[0]), lead_rank);
+    // W is a constant: with 64-column tiles (few-row chains, where a kernel is a chain of latencies) the weight halves of the
+    // first tile's first ring stages are requested BEFORE the dependency wait, and the rest of this CTA's weight rows is pulled
+    // into L2, so that after the wait only A has to arrive.
+    int pre = 0;
+    if (BN == 64 && pair < total && p.pre_flags != 0) {
+      const int n0 = (pair % n_tiles) * BN + static_cast<int>(rank) * (BN / 2);
+      pre = (p.pre_flags & 1) ? (k_blocks < STAGES ? k_blocks : STAGES) : 0;
+      for (int kb = 0; kb < pre; ++kb) {
+        if (elect_one()) {
+          if (leader) mbar_arrive_expect_tx(&full_bar[kb], 2 * STAGE_BYTES);
+          tma_load_2d_pair(&tm_b, full_leader0 + kb * 8, smem + kb * STAGE_BYTES + A_BYTES, (kb_first + kb) * BK, n0);
+        }
+        __syncwarp();
+      }
+      if ((p.pre_flags & 2) && k_blocks > pre && lane == 0) {
+        // rows of this CTA's half tile, shared out over the K shares of the cluster (each row: K contiguous bf16)
+        constexpr int ROWS = BN / 2 / KS;
+        const int r0 = n0 + kq * ROWS;
+        const int rows = r0 + ROWS <= p.N ? ROWS : (p.N > r0 ? p.N - r0 : 0);
+        const uint8_t* src = static_cast<const uint8_t*>(p.w_ptr) + static_cast<size_t>(r0) * p.K * 2;
+        for (long long off = 0, bytes = static_cast<long long>(rows) * p.K * 2; off < bytes; off += 32768)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + off), "r"(static_cast<uint32_t>(bytes - off < 32768 ? bytes - off : 32768))
+                       : "memory");
+      }
+    }
+    pdl_wait();                // the predecessor's outputs (A) are complete and visible from here on
     for (int t = pair; t < total; t += n_pairs) {
       const int m0 = (t / n_tiles) * (2 * BM) + static_cast<int>(rank) * BM;
       const int n0 = (t % n_tiles) * BN + static_cast<int>(rank) * (BN / 2);
       for (int kb = 0; kb < k_blocks; ++kb) {
+        const bool w_there = t == pair && kb < pre;     // this stage's weights (and its expect) were issued ahead of the wait
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
           uint8_t* sa = smem + stage * STAGE_BYTES;
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);   // both CTAs' bytes land on this barrier
+          if (leader && !w_there) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);   // both CTAs' bytes land on this barrier
           const uint32_t full_leader = full_leader0 + stage * 8;
-          tma_load_2d_pair(&tm_a, full_leader, sa, kb * BK, m0);
-          tma_load_2d_pair(&tm_b, full_leader, sa + A_BYTES, kb * BK, n0);
+          tma_load_2d_pair(&tm_a, full_leader, sa, (kb_first + kb) * BK, m0);
+          if (!w_there) tma_load_2d_pair(&tm_b, full_leader, sa + A_BYTES, (kb_first + kb) * BK, n0);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
+    pdl_wait();
     // ------------------------------------------------ MMA issuer (leader CTA; whole warp loops, one elected lane issues)
     if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
@@ -344,8 +393,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
               // +32 B per K=16 slice inside the 128 B swizzle row (start address is in 16 B units)
               tc_mma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
             }
-            tc_commit_pair(&empty_bar[stage], 0x3);   // both CTAs' slots reusable once these MMAs retire
-            if (kb == k_blocks - 1) tc_commit_pair(&tfull_bar[acc], 0x3);   // accumulator complete in both CTAs
+            tc_commit_pair(&empty_bar[stage], pair_mask);   // both CTAs' slots reusable once these MMAs retire
+            if (kb == k_blocks - 1) tc_commit_pair(&tfull_bar[acc], pair_mask);   // accumulator complete in both CTAs
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -355,6 +404,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
   } else {
     // ------------------------------------------------ epilogue warps (both CTAs)
+    pdl_wait();                         // residual stream / statistics of the predecessor are complete and visible from here on
     const int ew = warp - 2;            // 0..7
     const int quarter = warp & 3;       // TMEM lane quarter this warp may read
     const int part = ew >> 2;           // which column chunks of the 256-wide tile: 0 -> 0..2, 1 -> 3..5, 2 -> 6..7
@@ -363,19 +413,79 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     constexpr int CHUNKS = BN / 32, GROUPS = EPI_WARPS / 4;
     const int c_begin = (part * CHUNKS + GROUPS - 1) / GROUPS, c_end = ((part + 1) * CHUNKS + GROUPS - 1) / GROUPS;
     uint8_t* stg = epi_stage + ew * EPI_STAGE_BYTES;
-    const uint32_t tempty_leader0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
-    const uint32_t tempty_leader1 = mapa_shared(smem_u32(&tempty_bar[1]), 0);
+    const uint32_t tempty_leader0 = mapa_shared(smem_u32(&tempty_bar[0]), lead_rank);
+    const uint32_t tempty_leader1 = mapa_shared(smem_u32(&tempty_bar[1]), lead_rank);
     int acc = 0; uint32_t acc_phase = 0;
     float4 xnext[8];
-    if (MODE == VC_EPI_RESID_STATS && pair < total)
+    if (MODE == VC_EPI_RESID_STATS && KS == 1 && pair < total)
       resid_prefetch(p, lane, (pair / n_tiles) * (2 * BM) + static_cast<int>(rank) * BM + quarter * 32, (pair % n_tiles) * BN + c_begin * 32, xnext);
     for (int t = pair; t < total; t += n_pairs) {
       const int m0 = (t / n_tiles) * (2 * BM) + static_cast<int>(rank) * BM;
       const int n0 = (t % n_tiles) * BN;
+      const int row_base = m0 + quarter * 32;
+      float2 st[8];
+      if (MODE >= VC_EPI_LNF_BIAS && MODE <= VC_EPI_LNF_GELU_TANH) {
+        // the rows' LayerNorm statistics, fetched while the MMAs of the tile run
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = row_base + i * 4 + (lane >> 3);
+          st[i] = __ldcg(p.stats + (row < p.M ? row : 0));     // written by the kernel before this one: not the read-only path
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row_base = m0 + quarter * 32;
-      if (MODE == VC_EPI_RESID_STATS) {
+      if constexpr (KS > 1) {
+        constexpr int QPO = 4 / KS;                       // TMEM lane quarters (32 rows) per owning CTA
+        const int owner = quarter / QPO;                  // K share index of the CTA that finishes these rows (same row half)
+        const bool mine = owner == kq;
+        float4 xcur[8];
+        if (c_begin < c_end) {
+          const int c = c_begin;                          // 64-column tile: one 32-column chunk per warp with a chunk
+          if (mine) resid_prefetch(p, lane, row_base, n0 + c * 32, xcur);      // in flight while the partials travel
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, r);
+          tmem_ld_wait();
+          // this lane's row (quarter * 32 + lane of the row half), 32 columns -> slot kq of the owner's receive buffer
+          const uint32_t dst = mapa_shared(smem_u32(red_buf + ((kq * QPO + (quarter - owner * QPO)) * 32 + lane) * RED_PITCH + c * 32),
+                                           static_cast<uint32_t>(owner * 2) + rank);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + j * 16), "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]),
+                         "r"(r[4 * j + 3])
+                         : "memory");
+          mbar_arrive_cluster(mapa_shared(smem_u32(red_bar), static_cast<uint32_t>(owner * 2) + rank));   // releases this lane's stores
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+        if (c_begin < c_end && mine) {
+          const int c = c_begin;
+          mbar_wait_cluster(red_bar, 0);                  // all KS x QPO x 2 blocks of this CTA's rows are in
+          const float* src = red_buf + ((quarter - owner * QPO) * 32 + lane) * RED_PITCH + c * 32;
+          float4 a[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = *reinterpret_cast<const float4*>(src + 4 * j);
+#pragma unroll
+          for (int s2 = 1; s2 < KS; ++s2) {                // fixed order: K shares 0, 1, ...
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = *reinterpret_cast<const float4*>(src + s2 * QPO * 32 * RED_PITCH + 4 * j);
+              a[j].x += b.x; a[j].y += b.y; a[j].z += b.z; a[j].w += b.w;
+            }
+          }
+          uint32_t r[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            r[4 * j] = __float_as_uint(a[j].x); r[4 * j + 1] = __float_as_uint(a[j].y);
+            r[4 * j + 2] = __float_as_uint(a[j].z); r[4 * j + 3] = __float_as_uint(a[j].w);
+          }
+          const int col0 = n0 + c * 32;
+          if (col0 < p.N && row_base < p.M) {
+            epilogue_park(stg, lane, r);
+            epilogue_block_resid(p, stg, lane, row_base, col0, xcur);
+          }
+        }
+      } else if (MODE == VC_EPI_RESID_STATS) {
 #pragma unroll 1
         for (int c = c_begin; c < c_end; ++c) {
           uint32_t r[32];
@@ -400,14 +510,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
       } else {
-        float2 st[8];
-        if (MODE >= VC_EPI_LNF_BIAS) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = row_base + i * 4 + (lane >> 3);
-            st[i] = __ldcg(p.stats + (row < p.M ? row : 0));     // written by the kernel before this one: not the read-only path
-          }
-        }
 #pragma unroll 1
         for (int c = c_begin; c < c_end; ++c) {
           const int col_in_tile = c * 32;
@@ -442,9 +544,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         const int parts = p.N >> 5;
         for (int row = static_cast<int>(threadIdx.x) - 64; row < p.M; row += EPI_WARPS * 32) {
           double sm = 0.0, sq = 0.0;
-          for (int c = 0; c < parts; ++c) {
-            const float2 v = __ldcg(p.pstats + static_cast<size_t>(c) * p.M + row);
-            sm += v.x; sq += v.y;
+          for (int c0 = 0; c0 < parts; c0 += 8) {           // eight loads in flight, summed in ascending chunk order
+            float2 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = c0 + k < parts ? __ldcg(p.pstats + static_cast<size_t>(c0 + k) * p.M + row) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { sm += v[k].x; sq += v[k].y; }
           }
           const double mean = sm / p.N;
           double var = sq / p.N - mean * mean;
@@ -483,15 +588,15 @@ int make_map(CUtensorMap* tm, const void* ptr, int rows, int K, int box_rows) { 
 
 int g_num_sms = 0;
 std::mutex g_cfg_mu;
-PerDeviceOnce g_attr_set[16][2];
+PerDeviceOnce g_attr_set[16][4];
 
-template <int MODE, int BN>
+template <int MODE, int BN, int KS = 1>
 int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t stream) {
   {
     std::lock_guard<std::mutex> lk(g_cfg_mu);
-    if (g_attr_set[MODE][BN == 256 ? 0 : 1].first()) {
-      VC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(MODE, BN)));
-      VC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE, BN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (g_attr_set[MODE][BN == 256 ? 0 : (KS == 1 ? 1 : (KS == 2 ? 2 : 3))].first()) {
+      VC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE, BN, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(MODE, BN, KS)));
+      VC_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE, BN, KS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
   }
   static const char* const kNames[] = {"gemm_bias", "gemm_gelu_erf", "gemm_gelu_tanh", "gemm_resid", "gemm_f32", "gemm_patch",
@@ -500,7 +605,8 @@ int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
     KernelScope ks(kNames[MODE], 2.0 * p.M * static_cast<double>(p.N) * p.K, stream);
     // programmatic dependent launch: inside the GPT-2 chains the next kernel's prologue overlaps this kernel's tail; after a
     // kernel that never triggers (the encoder's plain launches) it behaves like an ordinary launch
-    VC_CUDA_OK(launch_pdl(gemm_tcgen05_kernel<MODE, BN>, dim3(grid), dim3(gemm_threads(MODE)), static_cast<size_t>(gemm_smem(MODE, BN)), stream, ta, tb, p));
+    VC_CUDA_OK(launch_pdl(gemm_tcgen05_kernel<MODE, BN, KS>, dim3(grid), dim3(gemm_threads(MODE)), static_cast<size_t>(gemm_smem(MODE, BN, KS)), stream, ta, tb,
+                          p));
   }
   VC_CUDA_OK(cudaGetLastError());
   return 0;
@@ -576,13 +682,15 @@ int gemm_bf16_ex(const void* A, const void* W, const float* bias, int M, int N, 
   CUtensorMap ta, tb;
   if (int e = make_map(&ta, A, M, K, BM)) return e;
   if (int e = make_map(&tb, W, N, K, BN / 2)) return e;
-  GemmParams p{M, N, K, mode, bias, out, ldo, aux, rows_per_group, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
+  GemmParams p{M, N, K, mode, bias, out, ldo, aux, rows_per_group, nullptr, nullptr, W, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
   if (ex != nullptr) {
     p.cs = ex->cs; p.stats = reinterpret_cast<const float2*>(ex->stats); p.xres = ex->xres;
     p.xb_out = static_cast<__nv_bfloat16*>(ex->xb_out);
     p.pstats = reinterpret_cast<float2*>(ex->pstats);
     p.stats_out = reinterpret_cast<float2*>(ex->stats_out); p.done = ex->done; p.eps = ex->eps;
   }
+  static const int pre_flags = getenv("VC_GEMM_PRE") ? atoi(getenv("VC_GEMM_PRE")) : 3;
+  p.pre_flags = pre_flags;
   const int total = m_tiles * ((N + BN - 1) / BN);   // pair tiles
   // VC_ENCODER_SMS=n leaves SMs free for kernels of another stream (the decode chain of the previous batch)
   static const int sm_cap = getenv("VC_ENCODER_SMS") ? atoi(getenv("VC_ENCODER_SMS")) : 0;
@@ -590,6 +698,16 @@ int gemm_bf16_ex(const void* A, const void* W, const float* bias, int M, int N, 
   if (total < pairs) pairs = total;
   if (max_ctas > 0 && 2 * pairs > max_ctas) pairs = max_ctas / 2 > 0 ? max_ctas / 2 : 1;
   const int grid = 2 * pairs;
+  if (mode == VC_EPI_RESID_STATS && BN == 64 && max_ctas <= 0 && sm_cap <= 0) {
+    // few column tiles (N = 768: 12 per row tile): split K over the CTA pairs of a cluster, one tile per cluster
+    static const int env_ks = getenv("VC_GEMM_KS") ? atoi(getenv("VC_GEMM_KS")) : 0;        // 1 = never split (A/B)
+    const int force_ks = ex != nullptr && ex->split_k > 0 ? ex->split_k : env_ks;
+    const int kb = K / BK;
+    int ks = total * 8 <= g_num_sms && kb % 4 == 0 ? 4 : (total * 4 <= g_num_sms && kb % 2 == 0 ? 2 : 1);
+    if (force_ks == 1 || ((force_ks == 2 || force_ks == 4) && kb % force_ks == 0)) ks = force_ks;
+    if (ks == 4) return launch_bn<VC_EPI_RESID_STATS, 64, 4>(ta, tb, p, total * 8, stream);
+    if (ks == 2) return launch_bn<VC_EPI_RESID_STATS, 64, 2>(ta, tb, p, total * 4, stream);
+  }
   switch (mode) {
     case VC_EPI_BIAS: return launch<VC_EPI_BIAS>(ta, tb, p, grid, BN, stream);
     case VC_EPI_BIAS_GELU_ERF: return launch<VC_EPI_BIAS_GELU_ERF>(ta, tb, p, grid, BN, stream);

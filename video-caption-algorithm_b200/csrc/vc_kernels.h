@@ -62,6 +62,7 @@ struct GemmExtra {
   float* stats_out;      // RESID_STATS, optional (few rows): float2 (mean, rstd) [M] written by the last CTA to finish ...
   unsigned int* done;    // ... which needs a device counter that is zero before the launch (it is reset to zero at the end)
   float eps;
+  int split_k;           // RESID_STATS with 64-column tiles: 0 = chosen from the shape, 1 / 2 / 4 = forced (tests, A/B)
 };
 int gemm_bf16_ex(const void* A, const void* W, const float* bias, int M, int N, int K, int mode, void* out, int ldo,
                  const float* aux, int rows_per_group, int max_ctas, const GemmExtra* ex, cudaStream_t stream);

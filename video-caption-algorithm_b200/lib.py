@@ -21,7 +21,7 @@ HEADERS = ["vc_common.cuh", "vc_kernels.h", "../../include/vcb200.h"]
 # -cudart shared: the runtime is the process's libcudart.so (torch ships one), not a private static copy inside the library
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
-ABI_VERSION = 4          # == vc_abi_version(); bumped with every struct / signature change (include/vcb200.h)
+ABI_VERSION = 5          # == vc_abi_version(); bumped with every struct / signature change (include/vcb200.h)
 
 
 class VcError(RuntimeError):
@@ -133,6 +133,7 @@ _SIGNATURES = {
     "vc_preprocess_u8": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "vc_patchify_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "vc_gemm_bf16": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p]),
+    "vc_gemm_resid_stats": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _f, _i, _p]),
     "vc_layernorm_f32_bf16": (_i, [_p, _p, _p, _p, _i, _i, _f, _p]),
     "vc_vit_attention": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "vc_vit_attention_mma_sync": (_i, [_p, _p, _i, _i, _i, _i, _p]),
