@@ -344,7 +344,7 @@ def run_b200(args):
     ids, lens = pipe.result(ticket, host=False)
     live = lib.vc_launch_count() - l0
     clocks = sampler.stop()
-    launches = live + (args.steps // group) * graph_nodes
+    launches = live + -(-args.steps // group) * graph_nodes     # one graph replay per complete group + one for the remainder (same kernel sequence)
     # the gathered ids are kept and checked (outside the timed region): block r of the buffer is rank r's own batch, and every
     # rank holds the same buffer
     torch.cuda.synchronize()
@@ -400,7 +400,7 @@ def run_b200(args):
         n_dec = min(B, 64)                                # BASELINE metric: p50 decode-step latency at 64 sequences
         prefix = prefix[:n_dec].contiguous()
         step_p50 = step_latency(prefix)
-        step_p50_256 = step_latency(prefix.repeat(256 // n_dec, 1, 1), warm=3, iters=10)     # the grouped chain the pipeline runs
+        step_p50_256 = step_latency(prefix.repeat(256 // n_dec, 1, 1), warm=3, iters=10)     # the grouped chain the pipeline runs (tcgen05 GEMMs)
         # reference-style number: the benchmark's python loop over gpt2(inputs_embeds=..., past_key_values=...) with a host
         # sync after every step (benchmark_baseline.py:194-221), through the adapter's reference surface
         import time as _time
@@ -464,7 +464,8 @@ def run_b200(args):
                   "frac": round(step_bytes / (step_p50 * 1e-6) / 1e9 / pk["hbm"], 4), "n_seq": n_dec, "S_range": [P0, P0 + n_new - 1],
                   "step_p50_us_256_rows": round(step_p50_256, 1),
                   "frac_256_rows": round(step_bytes_256 / (step_p50_256 * 1e-6) / 1e9 / pk["hbm"], 4),
-                  "chains": "<= 64 rows: decode_chain.cu (5 kernels per layer); beyond: split-K chain (8 per layer), which the pipeline's grouped decode uses",
+                  "chains": "<= 64 rows: decode_chain.cu (weights in registers, 5 kernels per layer); 65-127: split-K weight streaming (8 per layer); "
+                            ">= 128 rows: tcgen05 GEMMs with 64-column tiles, LayerNorm folded (5 per layer) - the pipeline's grouped decode",
                   "step_synced_p50_us": round(step_synced_p50, 1), "how": "(graph replay of prefill+19 steps - graph replay of prefill) / 19, p50 of 50 iterations after 10 warm-ups; step_synced = the reference's python loop with a host sync per step through the adapter surface"}
         line = {
             "metric": "captions/sec (16-frame clips)", "value": round(value, 2), "unit": "captions/s", "n_gpus": world,

@@ -56,7 +56,6 @@ struct Tile {
 // active), so they get 16 warps = two 32-column chunks each; the residual + statistics epilogue waits on HBM, keeps a block
 // of residual values in flight per warp (128 registers), and stays at 12 warps (chunks 0-2, 3-5, 6-7).
 __host__ __device__ constexpr int epi_warps(int mode) { return mode == VC_EPI_RESID_STATS ? 12 : 16; }   // 16 x 112 registers does not launch
-constexpr int EPI_WARPS_MAX = 16;
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // one 32x32 fp32 block per warp
 __host__ __device__ constexpr int gemm_threads(int mode) { return (2 + epi_warps(mode)) * 32; }
 // Split-K (KS CTA pairs of one cluster share a 64-column tile, each walks K/KS): a 4-stage ring is enough for K/KS, and every CTA
@@ -100,14 +99,6 @@ __device__ __forceinline__ void st_pred_v4(void* ptr, float4 v, bool ok) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %0, 0;\n\t@p st.global.v4.f32 [%1], {%2, %3, %4, %5};\n\t}" ::"r"(static_cast<uint32_t>(ok)), "l"(ptr),
                "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
-}
-__device__ __forceinline__ uint2 ld_pred_v2(const void* ptr, bool ok) {
-  uint2 v = make_uint2(0u, 0u);
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p ld.global.v2.b32 {%0, %1}, [%3];\n\t}"
-               : "+r"(v.x), "+r"(v.y)
-               : "r"(static_cast<uint32_t>(ok)), "l"(ptr)
-               : "memory");
-  return v;
 }
 __device__ __forceinline__ float4 ld_pred_v4(const void* ptr, bool ok) {
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -174,7 +165,7 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, uint8_t* stg
 // change from one column chunk to the next).
 template <int MODE>
 __device__ __forceinline__ void epilogue_block_lnf(const GemmParams& p, uint8_t* stg, int lane, int row_base, int col0, const uint32_t (&acc)[32],
-                                                   const float2 (&st)[8]) {
+                                                   const float2 (&st)[8], const float4 b, const float4 c) {
   const uint32_t sbase = smem_u32(stg);
   const int cc = lane & 7, rsub = lane >> 3;
   const int col = col0 + cc * 4;
@@ -185,8 +176,6 @@ __device__ __forceinline__ void epilogue_block_lnf(const GemmParams& p, uint8_t*
                  : "memory");
   }
   __syncwarp();
-  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-  const float4 c = __ldg(reinterpret_cast<const float4*>(p.cs + col));
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int rr = i * 4 + rsub;
@@ -233,11 +222,11 @@ __device__ __forceinline__ void epilogue_park(uint8_t* stg, int lane, const uint
   }
   __syncwarp();
 }
-__device__ __forceinline__ void epilogue_block_resid(const GemmParams& p, uint8_t* stg, int lane, int row_base, int col0, const float4 (&xv)[8]) {
+__device__ __forceinline__ void epilogue_block_resid(const GemmParams& p, uint8_t* stg, int lane, int row_base, int col0, const float4 (&xv)[8],
+                                                     const float4 b) {
   const uint32_t sbase = smem_u32(stg);
   const int cc = lane & 7, rsub = lane >> 3;
   const int col = col0 + cc * 4;
-  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int rr = i * 4 + rsub;
@@ -482,17 +471,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           const int col0 = n0 + c * 32;
           if (col0 < p.N && row_base < p.M) {
             epilogue_park(stg, lane, r);
-            epilogue_block_resid(p, stg, lane, row_base, col0, xcur);
+            epilogue_block_resid(p, stg, lane, row_base, col0, xcur, __ldg(reinterpret_cast<const float4*>(p.bias + col0 + (lane & 7) * 4)));
           }
         }
       } else if (MODE == VC_EPI_RESID_STATS) {
 #pragma unroll 1
         for (int c = c_begin; c < c_end; ++c) {
+          const int col0 = n0 + c * 32;
+          const bool live = col0 < p.N && row_base < p.M;
+          float4 fb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live) fb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + (lane & 7) * 4));     // travels under the TMEM load
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, r);
           tmem_ld_wait();
-          const int col0 = n0 + c * 32;
-          const bool live = col0 < p.N && row_base < p.M;
           if (live) epilogue_park(stg, lane, r);
           float4 xcur[8];
 #pragma unroll
@@ -504,7 +495,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             const int t2 = t + n_pairs;
             resid_prefetch(p, lane, (t2 / n_tiles) * (2 * BM) + static_cast<int>(rank) * BM + quarter * 32, (t2 % n_tiles) * BN + c_begin * 32, xnext);
           }
-          if (live) epilogue_block_resid(p, stg, lane, row_base, col0, xcur);
+          if (live) epilogue_block_resid(p, stg, lane, row_base, col0, xcur, fb);
         }
         tc_fence_before();
         __syncwarp();
@@ -513,12 +504,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 #pragma unroll 1
         for (int c = c_begin; c < c_end; ++c) {
           const int col_in_tile = c * 32;
+          const int col0 = n0 + col_in_tile;
+          float4 fb = make_float4(0.f, 0.f, 0.f, 0.f), fc = fb;
+          if (MODE >= VC_EPI_LNF_BIAS && col0 < p.N) {            // the chunk's folded bias and column sums travel under the TMEM load
+            fb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + (lane & 7) * 4));
+            fc = __ldg(reinterpret_cast<const float4*>(p.cs + col0 + (lane & 7) * 4));
+          }
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_in_tile, r);
           tmem_ld_wait();
-          const int col0 = n0 + col_in_tile;
           if (col0 < p.N && row_base < p.M) {
-            if (MODE >= VC_EPI_LNF_BIAS) epilogue_block_lnf<MODE>(p, stg, lane, row_base, col0, r, st);
+            if (MODE >= VC_EPI_LNF_BIAS) epilogue_block_lnf<MODE>(p, stg, lane, row_base, col0, r, st, fb, fc);
             else epilogue_block<MODE>(p, stg, lane, row_base, col0, r);
           }
         }
