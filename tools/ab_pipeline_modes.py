@@ -13,7 +13,7 @@ a = synthetic.ARCHS["vit_b16_gpt2"]
 dev = torch.device("cuda", 0)
 m = B200CaptionModel(synthetic.make_state_dict(a, seed=1234), dev, vit_heads=a.vit_heads, gpt_heads=a.gpt_heads, chunk_frames=1024)
 devf = synthetic.make_batch_u8(0, 64, 16).to(dev)
-MODES = [(4, True), (8, True), (2, True), (1, True), (4, False)]
+MODES = [(4, True), (4, False)]
 pipes = {}
 
 
