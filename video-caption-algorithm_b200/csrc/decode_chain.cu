@@ -32,6 +32,9 @@
 
 namespace vc {
 
+int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* ptr, int rows, int K, int box_rows);
+int make_tmap_bf16_kmajor_ld(CUtensorMap* tm, const void* ptr, int rows, int K, long long ld, int box_rows);
+
 #define VC_LAUNCH(name, work, stream, ...)        \
   do {                                            \
     vc::KernelScope _ks(name, work, stream);      \
@@ -283,6 +286,8 @@ dc_fullk_kernel(const __nv_bfloat16* __restrict__ hb, const float2* __restrict__
     cp_async_wait<1>();                                // this thread's pieces of chunk c (the newest group may still fly)
     __syncthreads();                                   // ... and everybody else's
     if (c == 0) tr.mark(3);
+    // this thread's epilogue row: (mean, rstd) from the partials that arrived with the chunk, computed under the MMAs
+    const float2 mr = row_mean_rstd_smem(s_part + (c & 1) * DC_MAX_PARTS * 32, n_part, 32, e_row, K, eps);
     const uint32_t xb0 = smem_u32(xs + (c & 1) * XBUF) + kbyte;
     float acc[2][NF][4];
 #pragma unroll
@@ -319,7 +324,6 @@ dc_fullk_kernel(const __nv_bfloat16* __restrict__ hb, const float2* __restrict__
     if (c == 0) tr.mark(5);
     const int row = c * 32 + e_row;
     if (row < M) {
-      const float2 mr = row_mean_rstd_smem(s_part + (c & 1) * DC_MAX_PARTS * 32, n_part, 32, e_row, K, eps);
 #pragma unroll
       for (int j = 0; j < NF; ++j) {
         const float* rr = red + e_row * RP + e_f + 8 * j;
@@ -680,6 +684,197 @@ dc_lmhead_kernel(const __nv_bfloat16* __restrict__ hb, const float2* __restrict_
   tr.flush();
 }
 
+// ------------------------------------------------------------------------------------------------ lm_head on tcgen05
+// Same product and the same outputs as dc_lmhead_kernel, for up to 64 rows per row tile.  ncu on the mma.sync kernel: 8 warps of
+// dependent LDS -> HMMA chains keep the tensor pipe 26 % busy and issue on 22 % of the cycles — neither HBM nor L2 is the limit
+// (requesting the CTA's whole weight range into L2 ahead of time changes nothing): 23-27 us per step for 77 MB.  Here the
+// activations sit in shared memory ONCE as the A operand (64 rows x K, K-major, 128-byte swizzle: K/64 TMA boxes of 8 KB) and the
+// CTA's ~340 vocabulary rows stream through a 5-stage ring of [64 rows x 64 K] TMA boxes as the B operand of
+// tcgen05.mma (M = 128, N = 64, K = 16; accumulators of the CTA's up to six 64-column sub-tiles side by side in TMEM).  M = 128
+// with 64 real rows: the instruction reads 16 KB from each A box, i.e. it runs on into the next box (for the last one: into the B
+// ring), and accumulator lanes 64-127 hold garbage nobody reads — the M = 128 accumulator layout (row = TMEM lane) is the one the
+// rest of this code base uses, and a single-CTA M = 64 instruction takes the same time.  Four epilogue warps (two per lane
+// quarter, one 32-column chunk of every sub-tile each) apply the folded ln_f + bias to one row per thread and keep the running
+// (max, lowest index) while the next sub-tile's MMAs run; logits are stored only when a buffer is given.  Shared memory stays at
+// 141 KB so that these CTAs become resident beside the last fc2's (80 KB) — and request their first weight boxes and the L2
+// prefetch of the rest — while that kernel is still running.  Measured: 15-16 us from the dependency to the last candidate
+// (mma.sync kernel: 23-27), step p50 323 -> 314 us at 64 sequences; the kernel now runs at what HBM delivers (77 MB at ~5 TB/s).
+// Tried, none faster: a 12-stage ring without the co-residency (316 us); K blocks in the outer loop with A streamed through a
+// 4-deep ring and 13 weight boxes in flight (325 us); keeping the matrix in L2 across steps — evict_last / evict_first cache
+// hints on the weight loads, or the last layer's four kernels each prefetching a quarter of it — ncu (--cache-control none)
+// still shows 78 MB of DRAM reads inside this kernel: 77 MB does not stay in the 126 MB (two-partition) L2 under a 247 MB step.
+constexpr int LT_NT = 64;                      // vocabulary rows per sub-tile (UMMA N)
+constexpr int LT_SUB = 6;                      // sub-tiles per CTA: up to 384 rows (148 CTAs: 340)
+constexpr int LT_STAGES = 5;
+constexpr int LT_B_BYTES = LT_NT * 128;        // 8 KB per stage
+constexpr int LT_THREADS = 192;                // warps 0, 1, 4, 5: epilogue (lane quarters 0 and 1), warp 2: TMA, warp 3: MMA
+__host__ __device__ constexpr int lt_smem(int K) { return (K / 64) * 8192 + LT_STAGES * LT_B_BYTES + 2 * LT_SUB * LT_NT * 4 + 2 * 2 * 64 * 4 + 256 + 1024; }
+
+__global__ void __launch_bounds__(LT_THREADS, 1)
+dc_lmhead_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, int K, const float2* __restrict__ stat,
+                    int n_part, long long stat_plane, long long row_stride, long long row_offset, const __nv_bfloat16* __restrict__ W,
+                    const float* __restrict__ cs, const float* __restrict__ bf, int vocab, int vocab_pad, int n_rows, float eps,
+                    float* __restrict__ logits, long long ld, float* __restrict__ cand_v, int* __restrict__ cand_i) {
+  extern __shared__ uint8_t lt_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(lt_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int k_blocks = K >> 6;
+  uint8_t* sA = smem;                                            // [k_blocks][64 rows][128 B]
+  uint8_t* sB = smem + k_blocks * 8192;                          // [LT_STAGES][64 rows][128 B]
+  float* s_cs = reinterpret_cast<float*>(sB + LT_STAGES * LT_B_BYTES);   // [384]
+  float* s_bf = s_cs + LT_SUB * LT_NT;                           // [384]
+  float* s_bv = s_bf + LT_SUB * LT_NT;                           // [2 halves][64 rows]
+  int* s_bi = reinterpret_cast<int*>(s_bv + 2 * 64);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bi + 2 * 64);
+  uint64_t* empty_bar = full_bar + LT_STAGES;
+  uint64_t* a_full = empty_bar + LT_STAGES;
+  uint64_t* tfull = a_full + 1;                                  // [LT_SUB]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + LT_SUB);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * 64;
+  const int tiles = vocab_pad >> 4;
+  const int t_begin = static_cast<int>(static_cast<long long>(tiles) * blockIdx.x / gridDim.x);
+  const int t_end = static_cast<int>(static_cast<long long>(tiles) * (blockIdx.x + 1) / gridDim.x);
+  const int v0 = t_begin * 16, v1 = t_end * 16;                  // this CTA's vocabulary rows (host: v1 - v0 <= LT_SUB * LT_NT)
+  const int n_sub = (v1 - v0 + LT_NT - 1) / LT_NT;
+  const int total = n_sub * k_blocks;                            // ring stages this CTA walks
+  Trace tr(6);
+  pdl_launch_dependents();       // at entry (see dc_fullk_kernel)
+
+  if (tid == 0) {
+    for (int i = 0; i < LT_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(a_full, 1);
+    for (int i = 0; i < LT_SUB; ++i) mbar_init(&tfull[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 2 && lane == 0) { tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_w); }
+  if (warp == 3) tmem_alloc(tmem_slot, 512);
+  // folded ln_f constants of the CTA's columns (constants: before the dependency wait)
+  for (int i = tid; i < LT_SUB * LT_NT; i += LT_THREADS) {
+    const int col = v0 + i;
+    s_cs[i] = col < vocab_pad ? __ldg(cs + col) : 0.f;
+    s_bf[i] = col < vocab_pad ? __ldg(bf + col) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 2) {
+    // ------------------------------------------------ TMA producer: weights are constants, so the ring is filled and the rest of
+    // the CTA's weight range is requested into L2 before the dependency wait; the activations follow it
+    int it = 0;
+    for (; it < LT_STAGES && it < total; ++it) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full_bar[it], LT_B_BYTES);
+        tma_load_2d(&tm_w, &full_bar[it], sB + it * LT_B_BYTES, (it % k_blocks) * 64, v0 + (it / k_blocks) * LT_NT);
+      }
+      __syncwarp();
+    }
+    {
+      const uint8_t* wb = reinterpret_cast<const uint8_t*>(W) + static_cast<size_t>(v0) * K * 2;
+      const long long bytes = static_cast<long long>(v1 - v0) * K * 2;
+      for (long long off = static_cast<long long>(lane) * 16384; off < bytes; off += 32LL * 16384)
+        l2_prefetch(wb + off, static_cast<uint32_t>(bytes - off < 16384 ? bytes - off : 16384));
+    }
+    pdl_wait();
+    if (elect_one()) {
+      mbar_arrive_expect_tx(a_full, static_cast<uint32_t>(k_blocks) * 8192);
+      for (int kb = 0; kb < k_blocks; ++kb) tma_load_2d(&tm_a, a_full, sA + kb * 8192, kb * 64, m0);
+    }
+    __syncwarp();
+    int stage = it % LT_STAGES;
+    uint32_t phase = 0;                                          // parity of the ring pass whose slots are being refilled
+    for (; it < total; ++it) {
+      mbar_wait(&empty_bar[stage], phase);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full_bar[stage], LT_B_BYTES);
+        tma_load_2d(&tm_w, &full_bar[stage], sB + stage * LT_B_BYTES, (it % k_blocks) * 64, v0 + (it / k_blocks) * LT_NT);
+      }
+      __syncwarp();
+      if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(128, LT_NT);
+    constexpr uint64_t desc_hi = umma_desc_sw128_hi();
+    const uint32_t a_lo = (smem_u32(sA) & 0x3FFFFu) >> 4, b_lo = (smem_u32(sB) & 0x3FFFFu) >> 4;
+    mbar_wait(a_full, 0);
+    tc_fence_after();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int sub = 0; sub < n_sub; ++sub) {
+      const uint32_t d_tmem = tmem_base + sub * LT_NT;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t da = desc_hi | (a_lo + kb * (8192 >> 4));
+          const uint64_t db = desc_hi | (b_lo + stage * (LT_B_BYTES >> 4));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          tc_commit(&empty_bar[stage]);
+          if (kb == k_blocks - 1) tc_commit(&tfull[sub]);
+        }
+        __syncwarp();
+        if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue: one row per thread
+    pdl_wait();
+    const int quarter = warp & 3;          // 0 / 1: accumulator lanes (= rows) 32 quarter .. + 31
+    const int half = warp >> 2;            // which 32-column chunk of every 64-column sub-tile
+    const int rr = quarter * 32 + lane, row = m0 + rr;
+    const int rowc = row < n_rows ? row : n_rows - 1;
+    const float2 mr = row_mean_rstd(stat, n_part, stat_plane, rowc * row_stride + row_offset, K, eps);
+    float best = -INFINITY;
+    int best_i = 0x7fffffff;
+    tr.mark(2);
+    for (int sub = 0; sub < n_sub; ++sub) {
+      mbar_wait(&tfull[sub], 0);
+      tc_fence_after();
+      if (sub == 0) tr.mark(3);
+      const int ci = sub * LT_NT + half * 32;             // column index inside the CTA's range
+      if (v0 + ci >= v1) continue;
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + ci, r);
+      tmem_ld_wait();
+      float y[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        y[j] = mr.y * (__uint_as_float(r[j]) - mr.x * s_cs[ci + j]) + s_bf[ci + j];
+        const int col = v0 + ci + j;
+        if (col < vocab && col < v1 && y[j] > best) { best = y[j]; best_i = col; }       // increasing index, strict '>'
+      }
+      if (logits != nullptr && row < n_rows) {
+        float* o = logits + static_cast<size_t>(row) * ld + v0 + ci;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          if (v0 + ci + j < v1) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+      }
+    }
+    tc_fence_before();
+    s_bv[half * 64 + rr] = best;
+    s_bi[half * 64 + rr] = best_i;
+    asm volatile("bar.sync 1, 128;" ::: "memory");                 // the four epilogue warps
+    if (half == 0 && row < n_rows) {
+      const float ov = s_bv[64 + rr];
+      const int oi = s_bi[64 + rr];
+      if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+      cand_v[static_cast<size_t>(row) * gridDim.x + blockIdx.x] = best;
+      cand_i[static_cast<size_t>(row) * gridDim.x + blockIdx.x] = best_i;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+  tr.flush();
+}
+
 // ------------------------------------------------------------------------------------------------ selection
 __device__ __forceinline__ int block_argmax_cands(const float* __restrict__ v, const int* __restrict__ idx, int n) {
   __shared__ float s_v[8];
@@ -910,6 +1105,22 @@ int chain_layers(const VcGptWeights* w, const ChainBuffers& b, int n_seq, int L,
   const int G = chain_lmhead_ctas();
   const dim3 grid(G, (n_seq + 63) / 64);
   const auto* lw = static_cast<const __nv_bfloat16*>(w->lmh_w);
+  // tcgen05 version (dc_lmhead_tc_kernel) when every CTA's vocabulary range fits its TMEM accumulators; VC_LMHEAD_TC=0: A/B switch
+  static const bool tc_off = getenv("VC_LMHEAD_TC") != nullptr && atoi(getenv("VC_LMHEAD_TC")) == 0;
+  const int max_range = (((w->vocab_pad >> 4) + G - 1) / G) * 16;
+  if (!tc_off && H % 64 == 0 && max_range <= LT_SUB * LT_NT && lt_smem(H) <= 227 * 1024) {
+    CUtensorMap ta, tw;
+    // A: row r = last position of sequence r; rows beyond n_seq read as zeros
+    if ((e = make_tmap_bf16_kmajor_ld(&ta, hb + static_cast<size_t>(L - 1) * H, n_seq, H, static_cast<long long>(L) * H, 64))) return e;
+    if ((e = make_tmap_bf16_kmajor(&tw, lw, w->vocab_pad, H, LT_NT))) return e;
+    if ((e = set_smem(dc_lmhead_tc_kernel, static_cast<size_t>(lt_smem(H))))) return e;
+    VC_LAUNCH("dc_lm_head_tc", static_cast<double>(w->vocab_pad) * H * 2.0, s,
+              VC_CUDA_OK(launch_pdl(dc_lmhead_tc_kernel, grid, dim3(LT_THREADS), static_cast<size_t>(lt_smem(H)), s, ta, tw, H, stat, parts,
+                                    static_cast<long long>(M), static_cast<long long>(L), static_cast<long long>(L - 1), lw, w->lmh_cs, w->lmh_b,
+                                    w->vocab, w->vocab_pad, n_seq, eps, logits, ld, b.cand_v, b.cand_i)));
+    VC_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   if (H == 768) {
     constexpr size_t smem = 64 * (768 * 2 + 64) + 64 * 8 + DC_MAX_PARTS * 64 * 8 + 2 * DC_WARPS * 64 * 4;
     if ((e = set_smem(dc_lmhead_kernel<3>, smem))) return e;

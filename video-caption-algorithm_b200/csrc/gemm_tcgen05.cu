@@ -632,6 +632,23 @@ int make_tmap_bf16_kmajor(CUtensorMap* tm, const void* ptr, int rows, int K, int
   return 0;
 }
 
+// Same, rows `ld` elements apart (ld >= K): the last position of every sequence of [n_seq, L, K] activations (lm_head, decode_chain.cu).
+int make_tmap_bf16_kmajor_ld(CUtensorMap* tm, const void* ptr, int rows, int K, long long ld, int box_rows) {
+  VC_REQUIRE(get_encode() == 0, "cuTensorMapEncodeTiled entry point not found (no CUDA driver?)");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%lld box_rows=%d ptr=%p", static_cast<int>(r), rows, K, ld, box_rows, ptr);
+    return -3;
+  }
+  return 0;
+}
+
 static int current_sms() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
