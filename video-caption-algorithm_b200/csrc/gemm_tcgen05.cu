@@ -446,7 +446,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+        if (lane == 0) mbar_arrive_cluster_signal(acc ? tempty_leader1 : tempty_leader0);
         if (c_begin < c_end && mine) {
           const int c = c_begin;
           mbar_wait_cluster(red_bar, 0);                  // all KS x QPO x 2 blocks of this CTA's rows are in
@@ -499,7 +499,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+        if (lane == 0) mbar_arrive_cluster_signal(acc ? tempty_leader1 : tempty_leader0);
       } else {
 #pragma unroll 1
         for (int c = c_begin; c < c_end; ++c) {
@@ -520,7 +520,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+        if (lane == 0) mbar_arrive_cluster_signal(acc ? tempty_leader1 : tempty_leader0);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }

@@ -189,6 +189,13 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Same, as a pure signal (CTA-scope release): nothing this thread wrote to memory has to be visible to the waiter.  The
+// cluster-scope release above compiles to MEMBAR.ALL.GPU, i.e. the warp first waits for every global store it has in flight
+// to be acknowledged — ncu showed the GEMM's epilogue warps stalled on exactly that once per tile (the "accumulator drained"
+// arrive only has to follow the TMEM loads, which tcgen05.wait::ld + tcgen05.fence::before_thread_sync already order).
+__device__ __forceinline__ void mbar_arrive_cluster_signal(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
