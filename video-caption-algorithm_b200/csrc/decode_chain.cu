@@ -1106,7 +1106,8 @@ int chain_layers(const VcGptWeights* w, const ChainBuffers& b, int n_seq, int L,
   const dim3 grid(G, (n_seq + 63) / 64);
   const auto* lw = static_cast<const __nv_bfloat16*>(w->lmh_w);
   // tcgen05 version (dc_lmhead_tc_kernel) when every CTA's vocabulary range fits its TMEM accumulators; VC_LMHEAD_TC=0: A/B switch
-  static const bool tc_off = getenv("VC_LMHEAD_TC") != nullptr && atoi(getenv("VC_LMHEAD_TC")) == 0;
+  const char* tc_env = getenv("VC_LMHEAD_TC");                 // read per call: the test flips it
+  const bool tc_off = tc_env != nullptr && atoi(tc_env) == 0;
   const int max_range = (((w->vocab_pad >> 4) + G - 1) / G) * 16;
   if (!tc_off && H % 64 == 0 && max_range <= LT_SUB * LT_NT && lt_smem(H) <= 227 * 1024) {
     CUtensorMap ta, tw;
