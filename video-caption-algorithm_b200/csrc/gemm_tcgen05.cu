@@ -10,7 +10,7 @@
 //   * one elected thread of the leader CTA issues tcgen05.mma (M=256, N=256, K=16); fp32
 //     accumulators live in TMEM (128 lanes x 256 columns per CTA), double-buffered so the epilogue
 //     of tile i overlaps the MMAs of tile i+1;
-//   * 12 epilogue warps per CTA read TMEM with tcgen05.ld (one accumulator row per thread),
+//   * 16 epilogue warps per CTA read TMEM with tcgen05.ld (one accumulator row per thread),
 //     transpose 32x32 blocks through swizzled shared memory and then apply bias / GELU /
 //     residual-add / patch-embed scatter with fully coalesced global accesses.
 //
@@ -26,6 +26,10 @@
 #include <mutex>
 #include <unordered_map>
 
+#ifndef VC_RESID_WARPS
+#define VC_RESID_WARPS 16
+#define VC_RESID_REGS 96
+#endif
 #ifndef VC_LNF_REGS
 #define VC_LNF_REGS 96
 #endif
@@ -53,9 +57,13 @@ struct Tile {
 };
 // Epilogue warps per CTA: a multiple of 4 (a warp reads the TMEM lane quarter warp % 4).  The bf16-output epilogues are
 // instruction-bound (ncu: the GELU epilogue executes 3x the instructions of the bias one and holds the tensor pipe at 68 %
-// active), so they get 16 warps = two 32-column chunks each; the residual + statistics epilogue waits on HBM, keeps a block
-// of residual values in flight per warp (128 registers), and stays at 12 warps (chunks 0-2, 3-5, 6-7).
-__host__ __device__ constexpr int epi_warps(int mode) { return mode == VC_EPI_RESID_STATS ? 12 : 16; }   // 16 x 112 registers does not launch
+// active), so they get 16 warps = two 32-column chunks each.  The residual + statistics epilogue waits on HBM and keeps a block
+// of residual values in flight per warp.  It ran with 12 warps x 128 registers (chunks 0-2, 3-5, 6-7: uneven) because
+// 16 warps x 104 registers "does not launch" — the limit is per SM sub-partition: 18 warps put 5 on one scheduler, and
+// 5 x 32 x 104 > 16,384 registers.  16 warps x 96 registers fits (one 8-byte spill) and measures 4 % faster over proj + fc2
+// (13.6-13.8 vs 14.1-14.8 ms per pass, two builds alternated on one box): 64 KB of residual reads in flight instead of 48 KB,
+// and two blocks for every warp.
+__host__ __device__ constexpr int epi_warps(int mode) { return mode == VC_EPI_RESID_STATS ? VC_RESID_WARPS : 16; }
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // one 32x32 fp32 block per warp
 __host__ __device__ constexpr int gemm_threads(int mode) { return (2 + epi_warps(mode)) * 32; }
 // Split-K (KS CTA pairs of one cluster share a 64-column tile, each walks K/KS): a 4-stage ring is enough for K/KS, and every CTA
@@ -261,7 +269,7 @@ __device__ __forceinline__ void epilogue_block_resid(const GemmParams& p, uint8_
 // per lane); the owner adds the KS partials in a fixed order and runs the ordinary residual + statistics epilogue on its
 // 128/KS rows.  One tile per cluster (grid = tiles x 2 KS CTAs).
 template <int MODE, int BN, int KS = 1>
-__global__ void __cluster_dims__(2 * KS, 1, 1) __maxnreg__(MODE == VC_EPI_RESID_STATS ? 128 : (MODE >= VC_EPI_LNF_BIAS ? VC_LNF_REGS : 80))   // x 448 / 576 threads <= 64K registers
+__global__ void __cluster_dims__(2 * KS, 1, 1) __maxnreg__(MODE == VC_EPI_RESID_STATS ? VC_RESID_REGS : (MODE >= VC_EPI_LNF_BIAS ? VC_LNF_REGS : 80))   // x 576 threads: 5 warps on one scheduler x 32 x 96 <= 16,384 registers
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmParams p) {
   static_assert(KS == 1 || (MODE == VC_EPI_RESID_STATS && BN == 64 && (KS == 2 || KS == 4)), "split-K: residual epilogue, 64-column tiles");
   extern __shared__ uint8_t smem_raw[];
