@@ -175,3 +175,25 @@ def test_frame_decode_pool_equals_single_thread_pil(tmp_path):
         assert np.array_equal(pool.decode(as_bytes).numpy(), want)
         with pytest.raises(ValueError):
             pool.decode([picks[0], picks[1][:3]])
+
+
+def test_epilogue_gelu_form_matches_erf_gelu():
+    """The GEMM epilogues evaluate nn.GELU() (erf form, torchvision MLPBlock / video_encoder.py:82-103) as
+    x * sigmoid(x (c1 + c3 x^2 + c5 x^4)) with x^2 clamped at 52.6 (csrc/vc_common.cuh: gelu_erf_fast).  The constants in the
+    kernel carry -log2(e); this restates the formula in fp32 and checks it against the erf GELU: max abs error <= 3e-5
+    (the tanh formula is 4.7e-4 away), exact limits for large |x|."""
+    import re
+    src = (ROOT / "video-caption-algorithm_b200" / "csrc" / "vc_common.cuh").read_text()
+    body = src[src.index("float gelu_erf_fast(float x)"):]
+    body = body[:body.index("\n}\n")]
+    consts = [float(v) for v in re.findall(r"(-?\d+\.\d+(?:e-?\d+)?)f", body)]
+    clamp, k5, k3, k1 = consts[0], consts[1], consts[2], consts[3]
+    assert clamp == 52.6 and k5 > 0 and k3 < 0 and k1 < 0, consts
+    x = torch.linspace(-30, 30, 600001, dtype=torch.float32)
+    x2 = torch.clamp(x * x, max=clamp)
+    q = (x2 * k5 + k3) * x2 + k1
+    got = x / (1.0 + torch.exp2(x * q))
+    ref = torch.nn.functional.gelu(x.double()).float()
+    assert (got - ref).abs().max().item() <= 3e-5
+    assert not torch.isnan(got).any()
+    assert got[0].item() == 0.0 and got[-1].item() == 30.0
