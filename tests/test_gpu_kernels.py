@@ -409,38 +409,44 @@ def test_decode_chain_fused_fc_variant_matches(lib):
 def test_lm_head_tcgen05_matches_mma_sync_version(lib):
     """dc_lmhead_tc_kernel (tcgen05, the default) against dc_lmhead_kernel (mma.sync, VC_LMHEAD_TC=0) through the public greedy
     call with teacher forcing: same logits to fp32 summation-order noise, same candidates -> same ids unless a near-tie flips;
-    61 sequences (rows 61-63 of the A box are out of bounds -> zero filled) and a full 64."""
+    61 sequences (rows 61-63 of the A box are out of bounds -> zero filled), a full 64, and 100 sequences on the same chain
+    (VC_DECODE_CHAIN=2: two row tiles, blockIdx.y = 1 reads rows 64-99)."""
     import os
     from vcb200 import synthetic
     from vcb200.model import B200CaptionModel
     a = synthetic.ARCHS["tiny"]
     m = B200CaptionModel(synthetic.make_state_dict(a, seed=1234), DEV, vit_heads=a.vit_heads, gpt_heads=a.gpt_heads)
     g = torch.Generator().manual_seed(11)
-    for n_seq in (61, 64):
-        prefix = (torch.randn(n_seq, a.prefix_len, a.gpt_dim, generator=g) * 0.3).to(DEV)
-        forced = torch.randint(0, 50000, (n_seq, 3), generator=g).int().to(DEV)
-        outs = []
-        for flag in (None, "0"):
-            if flag:
-                os.environ["VC_LMHEAD_TC"] = flag
-            else:
-                os.environ.pop("VC_LMHEAD_TC", None)
-            try:
-                ids, lens, lg = m.greedy_ids(prefix, None, 3, forced_ids=forced, keep_logits=True, use_graph=False)
-                torch.cuda.synchronize()
-                outs.append((ids.cpu().clone(), lg.float().cpu().clone(), lens.cpu().clone()))
-            finally:
-                os.environ.pop("VC_LMHEAD_TC", None)
-        # steps 1.. run on the few-row chain (the 5-position prefill of > 64 rows takes the GEMM chain in both runs)
-        assert (outs[0][1] - outs[1][1]).abs().max().item() < 2e-3, n_seq
-        assert (outs[0][0] == outs[1][0]).float().mean().item() >= 0.98, n_seq
-        # ids are the argmax of the logits each version produced itself (ties -> lowest index); a row that has emitted eos keeps
-        # eos from then on, whatever its logits say (benchmark_baseline.py:212-224)
-        for ids, lg, lens in outs:
-            live = torch.arange(3)[None, :] < lens[:, None].long()
-            am = lg.argmax(-1).t()
-            assert torch.equal(ids.long()[live], am[live]), n_seq
-            assert live[:, 1:].float().mean().item() > 0.9
+    try:
+        for n_seq in (61, 64, 100):
+            if n_seq > 64:
+                os.environ["VC_DECODE_CHAIN"] = "2"          # read per call: the few-row chain beyond 64 rows
+            prefix = (torch.randn(n_seq, a.prefix_len, a.gpt_dim, generator=g) * 0.3).to(DEV)
+            forced = torch.randint(0, 50000, (n_seq, 3), generator=g).int().to(DEV)
+            outs = []
+            for flag in (None, "0"):
+                if flag:
+                    os.environ["VC_LMHEAD_TC"] = flag
+                else:
+                    os.environ.pop("VC_LMHEAD_TC", None)
+                try:
+                    ids, lens, lg = m.greedy_ids(prefix, None, 3, forced_ids=forced, keep_logits=True, use_graph=False)
+                    torch.cuda.synchronize()
+                    outs.append((ids.cpu().clone(), lg.float().cpu().clone(), lens.cpu().clone()))
+                finally:
+                    os.environ.pop("VC_LMHEAD_TC", None)
+            # steps 1.. run on the few-row chain (the 5-position prefill of > 64 rows takes the GEMM chain in both runs)
+            assert (outs[0][1] - outs[1][1]).abs().max().item() < 2e-3, n_seq
+            assert (outs[0][0] == outs[1][0]).float().mean().item() >= 0.98, n_seq
+            # ids are the argmax of the logits each version produced itself (ties -> lowest index); a row that has emitted eos keeps
+            # eos from then on, whatever its logits say (benchmark_baseline.py:212-224)
+            for ids, lg, lens in outs:
+                live = torch.arange(3)[None, :] < lens[:, None].long()
+                am = lg.argmax(-1).t()
+                assert torch.equal(ids.long()[live], am[live]), n_seq
+                assert live[:, 1:].float().mean().item() > 0.9
+    finally:
+        os.environ.pop("VC_DECODE_CHAIN", None)
 
 
 def test_beam_update_kernel_equals_torch_bookkeeping():
