@@ -54,7 +54,8 @@ def parse():
     ap.add_argument("--chunk-frames", type=int, default=int(os.environ.get("VC_CHUNK_FRAMES", "1024")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--decode-group", type=int, default=4, help="encoder batches decoded together as one chain (CaptionPipeline)")
+    ap.add_argument("--decode-group", type=int, default=8, help="encoder batches decoded together as one chain (CaptionPipeline); "
+                    "8 -> 512 rows per chain: 41.4 ms per batch against 41.8 (6) and 42.4 (4), tools/ab_pipeline_modes.py 3 4,8,6")
     ap.add_argument("--global-batch", type=int, default=0, help="BASELINE configs[2]: total videos per step, sharded by video over the GPUs "
                                                                  "(512 -> 256 / 128 / 64 per GPU at 2 / 4 / 8); 0 = --batch per GPU (weak scaling)")
     ap.add_argument("--ref-sample", type=int, default=4, help="videos per step of the reference arm (bounded sample of the workload)")
@@ -274,7 +275,7 @@ def run_b200(args):
         B = args.global_batch // world                        # BASELINE configs[2]: 512 videos sharded by video
     else:
         B = args.batch
-    group = max(1, min(args.decode_group, 256 // B))          # sequences per decode chain <= 256 (CaptionPipeline.MAX_DECODE_ROWS)
+    group = max(1, min(args.decode_group, 512 // B))          # sequences per decode chain <= 512 (CaptionPipeline.MAX_DECODE_ROWS)
     sd = synthetic.make_state_dict(a, seed=1234)
     model = B200CaptionModel(sd, dev, vit_heads=a.vit_heads, gpt_heads=a.gpt_heads, chunk_frames=args.chunk_frames)
     # this rank's shard: global video indices rank*B .. rank*B+B-1 (reproducible for any world size)
@@ -400,7 +401,9 @@ def run_b200(args):
         n_dec = min(B, 64)                                # BASELINE metric: p50 decode-step latency at 64 sequences
         prefix = prefix[:n_dec].contiguous()
         step_p50 = step_latency(prefix)
-        step_p50_256 = step_latency(prefix.repeat(256 // n_dec, 1, 1), warm=3, iters=10)     # the grouped chain the pipeline runs (tcgen05 GEMMs)
+        step_p50_256 = step_latency(prefix.repeat(256 // n_dec, 1, 1), warm=3, iters=10)     # the grouped chain (tcgen05 GEMMs) at 256 rows
+        rows_group = group * B                                                              # ... and at the rows the pipeline really groups
+        step_p50_group = step_p50_256 if rows_group == 256 else step_latency(prefix.repeat(max(rows_group // n_dec, 1), 1, 1), warm=3, iters=10)
         # reference-style number: the benchmark's python loop over gpt2(inputs_embeds=..., past_key_values=...) with a host
         # sync after every step (benchmark_baseline.py:194-221), through the adapter's reference surface
         import time as _time
@@ -464,6 +467,7 @@ def run_b200(args):
                   "frac": round(step_bytes / (step_p50 * 1e-6) / 1e9 / pk["hbm"], 4), "n_seq": n_dec, "S_range": [P0, P0 + n_new - 1],
                   "step_p50_us_256_rows": round(step_p50_256, 1),
                   "frac_256_rows": round(step_bytes_256 / (step_p50_256 * 1e-6) / 1e9 / pk["hbm"], 4),
+                  "step_p50_us_pipeline_group": round(step_p50_group, 1), "pipeline_group_rows": rows_group,
                   "chains": "<= 64 rows: decode_chain.cu (weights in registers, 5 kernels per layer); 65-127: split-K weight streaming (8 per layer); "
                             ">= 128 rows: tcgen05 GEMMs with 64-column tiles, LayerNorm folded (5 per layer) - the pipeline's grouped decode",
                   "step_synced_p50_us": round(step_synced_p50, 1), "how": "(graph replay of prefill+19 steps - graph replay of prefill) / 19, p50 of 50 iterations after 10 warm-ups; step_synced = the reference's python loop with a host sync per step through the adapter surface"}

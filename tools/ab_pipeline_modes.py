@@ -9,11 +9,12 @@ from vcb200 import synthetic
 from vcb200.model import B200CaptionModel
 
 rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+# optional: the decode groups to compare, e.g. "4,8" (each with the decode chain on its own stream) instead of the default pair
 a = synthetic.ARCHS["vit_b16_gpt2"]
 dev = torch.device("cuda", 0)
 m = B200CaptionModel(synthetic.make_state_dict(a, seed=1234), dev, vit_heads=a.vit_heads, gpt_heads=a.gpt_heads, chunk_frames=1024)
 devf = synthetic.make_batch_u8(0, 64, 16).to(dev)
-MODES = [(4, True), (4, False)]
+MODES = [(int(g), True) for g in sys.argv[2].split(",")] if len(sys.argv) > 2 else [(4, True), (4, False)]
 pipes = {}
 
 
